@@ -1,0 +1,139 @@
+/*
+ * bdeflate.h — C ABI of the B200-native batch DEFLATE engine (libbdeflate.so).
+ *
+ * This is the drop-in boundary for the batch path of 404Setup/libdeflate-rsx:
+ * it is what a Rust `extern "C"` block behind src/batch.rs would bind (the
+ * binding is shown in INTEGRATION.md).  Plain pointers and sizes only.
+ *
+ * Data layout (the crate's existing GPU convention, src/batch_cuda.rs:57-87 and
+ * src/cuda/compress.cu:1-8): one flat byte buffer holding every stream back to
+ * back, `in_off[n+1]` byte offsets into it, one flat output slab with
+ * `out_off[n]` start offsets, and per-stream result arrays written by the
+ * device.  Nothing allocated by the library crosses the boundary except
+ * bdf_host_alloc() memory, which the caller frees with bdf_host_free().
+ *
+ * Error convention: the int return value is the CALL-level result (0 = the
+ * batch ran; negative = bad argument / CUDA failure — there is NO CPU
+ * fallback, unlike src/batch.rs:23-31).  Per-stream results are in-band, like
+ * the reference's empty Vec / None (src/batch.rs:52-53,95-96): status[i] uses
+ * the declaration order of DecompressResult (src/decompress/mod.rs:79-85) and
+ * out_size[i] is 0 for a failed stream.
+ */
+#ifndef BDEFLATE_H
+#define BDEFLATE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BDF_VERSION 0x000100 /* 0.1.0 */
+
+/* Framing.  src/batch.rs only speaks raw DEFLATE; zlib and gzip follow
+ * Compressor::compress_zlib/_gzip (src/compress/mod.rs:2248-2357) and
+ * Decompressor::decompress_zlib/_gzip (src/decompress/mod.rs:1074-1240). */
+enum bdf_format { BDF_RAW = 0, BDF_ZLIB = 1, BDF_GZIP = 2 };
+
+/* Per-stream status == DecompressResult order; compression uses OK and
+ * INSUFFICIENT_SPACE (CompressResult, src/compress/mod.rs:238-241). */
+enum bdf_status {
+    BDF_OK = 0,
+    BDF_BAD_DATA = 1,
+    BDF_SHORT_OUTPUT = 2, /* declared by the reference, never produced */
+    BDF_INSUFFICIENT_SPACE = 3,
+    BDF_SHORT_INPUT = 4
+};
+
+/* Call-level errors. */
+enum bdf_error {
+    BDF_E_OK = 0,
+    BDF_E_ARG = -1,         /* null pointer, unknown format / level / kind */
+    BDF_E_CUDA = -2,        /* a CUDA runtime call failed; see bdf_last_error */
+    BDF_E_NOMEM = -3,       /* device or pinned allocation failed */
+    BDF_E_UNSUPPORTED = -4  /* valid request this build does not implement */
+};
+
+enum bdf_checksum_kind { BDF_ADLER32 = 0, BDF_CRC32 = 1 };
+
+typedef struct bdf_ctx bdf_ctx;
+
+/* Library / device lifetime.  A ctx owns one CUDA stream, its scratch memory
+ * and staging buffers on `device`; calls on one ctx are serialised by an
+ * internal mutex, so a ctx may be shared between threads the way
+ * BatchCompressor is `Sync` (src/batch.rs:5-18), and several ctxs (one per
+ * GPU) may be driven concurrently. */
+int bdf_version(void);
+int bdf_device_count(void);
+int bdf_ctx_create(int device, bdf_ctx **ctx);
+void bdf_ctx_destroy(bdf_ctx *ctx);
+const char *bdf_last_error(const bdf_ctx *ctx);
+/* Number of engine kernels launched through this ctx so far. */
+uint64_t bdf_kernel_launches(const bdf_ctx *ctx);
+/* Device time (ms, CUDA events on the ctx stream) of the kernels of the last
+ * *_host call; 0 if none. */
+float bdf_last_kernel_ms(const bdf_ctx *ctx);
+
+/* Pinned host memory for the *_host entry points (pageable memory also works,
+ * through the driver's staging copies). */
+void *bdf_host_alloc(size_t bytes);
+void bdf_host_free(void *p);
+
+/* Compressor::{deflate,zlib,gzip}_compress_bound, src/compress/mod.rs:2236-2246:
+ * len + (len / 65535 + 1) * 5 + 10, + 6 (zlib) or + 18 (gzip). */
+size_t bdf_compress_bound(int format, size_t len);
+
+/*
+ * BatchDecompressor::decompress_batch (src/batch.rs:74-101).
+ *   stream i : in[in_off[i] .. in_off[i+1])  ->  out[out_off[i] ..), at most max_out[i] bytes
+ *   out_size[i] : bytes produced (0 on failure); status[i] : bdf_status
+ *   checksum[i] (may be NULL): Adler-32 (zlib) / CRC-32 (gzip) of the output, 0 for raw
+ * Like the reference, trailing input after the final block is ignored and
+ * producing fewer than max_out[i] bytes is success.
+ * *_device: every pointer is device memory valid on the ctx's device; the
+ * work is enqueued on `stream` (a cudaStream_t, NULL = the ctx stream) and
+ * the call returns without synchronising.  *_host: every pointer is host
+ * memory; the call copies in, runs, copies out and returns when the results
+ * are in place.
+ */
+int bdf_decompress_batch_device(bdf_ctx *ctx, int format, const uint8_t *in,
+                                const uint64_t *in_off, size_t n, uint8_t *out,
+                                const uint64_t *out_off, const uint64_t *max_out,
+                                uint64_t *out_size, uint32_t *checksum,
+                                int32_t *status, void *stream);
+int bdf_decompress_batch_host(bdf_ctx *ctx, int format, const uint8_t *in,
+                              const uint64_t *in_off, size_t n, uint8_t *out,
+                              const uint64_t *out_off, const uint64_t *max_out,
+                              uint64_t *out_size, uint32_t *checksum,
+                              int32_t *status);
+
+/*
+ * BatchCompressor::compress_batch (src/batch.rs:20-58) for `level` 0..12
+ * (Compressor::new, src/compress/mod.rs:459-507; values above 12 behave as 12).
+ * Stream i may use up to bdf_compress_bound(format, len_i) bytes at
+ * out + out_off[i]; a stream whose encoding does not fit fails with
+ * BDF_INSUFFICIENT_SPACE and out_size[i] = 0 — the reference has no
+ * stored-block fallback (src/compress/mod.rs:641-644).
+ */
+int bdf_compress_batch_device(bdf_ctx *ctx, int level, int format,
+                              const uint8_t *in, const uint64_t *in_off, size_t n,
+                              uint8_t *out, const uint64_t *out_off,
+                              uint64_t *out_size, int32_t *status, void *stream);
+int bdf_compress_batch_host(bdf_ctx *ctx, int level, int format, const uint8_t *in,
+                            const uint64_t *in_off, size_t n, uint8_t *out,
+                            const uint64_t *out_off, uint64_t *out_size,
+                            int32_t *status);
+
+/* adler32(1, data) / crc32(0, data) per stream (src/adler32/mod.rs:114-152,
+ * src/crc32/mod.rs:331-365). */
+int bdf_checksum_batch_device(bdf_ctx *ctx, int kind, const uint8_t *in,
+                              const uint64_t *in_off, size_t n, uint32_t *out,
+                              void *stream);
+int bdf_checksum_batch_host(bdf_ctx *ctx, int kind, const uint8_t *in,
+                            const uint64_t *in_off, size_t n, uint32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDEFLATE_H */

@@ -1,0 +1,404 @@
+// bdeflate.cu — the C ABI of include/bdeflate.h: context, launches, host staging.
+//
+// Single translation unit: the kernels live in the .cuh files included below.
+// Built by libdeflate_rsx_b200/build.py (nvcc -gencode arch=compute_100a,code=sm_100a).
+// There is no CPU path here: every entry point either runs the CUDA kernels or
+// returns a negative bdf_error.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+#include <new>
+
+#include "../../include/bdeflate.h"
+#include "checksum.cuh"
+#include "inflate.cuh"
+#include "deflate.cuh"
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct bdf_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::mutex mu;
+    char err[320] = {0};
+    uint64_t launches = 0;
+    float last_ms = 0.f;
+    unsigned long long *d_counters = nullptr;   // work-queue heads, one slot per launch in flight
+    unsigned counter_slot = 0;
+    int inflate_blocks_per_sm[3] = {0, 0, 0};
+    bdf::DeflateScratch deflate_scratch;
+    DevBuf in, out, in_off, out_off, max_out, out_size, status, checksum;
+};
+
+namespace {
+
+constexpr unsigned NUM_COUNTER_SLOTS = 64;
+
+int fail(bdf_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        if (e != cudaSuccess)
+            snprintf(c->err, sizeof(c->err), "%s: %s", what, cudaGetErrorString(e));
+        else
+            snprintf(c->err, sizeof(c->err), "%s", what);
+    }
+    return code;
+}
+
+#define CK(call)                                                     \
+    do {                                                             \
+        cudaError_t e_ = (call);                                     \
+        if (e_ != cudaSuccess) return fail(ctx, BDF_E_CUDA, #call, e_); \
+    } while (0)
+
+int ensure(bdf_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    if (b.cap >= bytes) return 0;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) return fail(ctx, BDF_E_NOMEM, "cudaMalloc", e);
+    b.cap = bytes;
+    return 0;
+}
+
+unsigned long long *next_counter(bdf_ctx *ctx, cudaStream_t s)
+{
+    unsigned long long *c = ctx->d_counters + (ctx->counter_slot++ % NUM_COUNTER_SLOTS);
+    cudaMemsetAsync(c, 0, sizeof(*c), s);
+    return c;
+}
+
+template <int FORMAT>
+int launch_inflate(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
+{
+    const size_t smem = sizeof(bdf::InflateWarpSmem) * bdf::INF_WARPS_PER_BLOCK;
+    int &bps = ctx->inflate_blocks_per_sm[FORMAT];
+    if (bps == 0) {
+        CK(cudaFuncSetAttribute(bdf::inflate_kernel<FORMAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(bdf::inflate_kernel<FORMAT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, bdf::inflate_kernel<FORMAT>,
+                                                         bdf::INF_WARPS_PER_BLOCK * 32, smem));
+        if (bps < 1) bps = 1;
+    }
+    unsigned long long want = ((unsigned long long)a.n + bdf::INF_WARPS_PER_BLOCK - 1) / bdf::INF_WARPS_PER_BLOCK;
+    unsigned long long full = (unsigned long long)ctx->sm_count * bps;
+    unsigned grid = (unsigned)(want < full ? want : full);
+    bdf::inflate_kernel<FORMAT><<<grid, bdf::INF_WARPS_PER_BLOCK * 32, smem, s>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+bool bad_format(int f) { return f != BDF_RAW && f != BDF_ZLIB && f != BDF_GZIP; }
+
+}  // namespace
+
+extern "C" {
+
+int bdf_version(void) { return BDF_VERSION; }
+
+int bdf_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int bdf_ctx_create(int device, bdf_ctx **out)
+{
+    if (!out) return BDF_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return BDF_E_CUDA;
+    bdf_ctx *ctx = new (std::nothrow) bdf_ctx();
+    if (!ctx) return BDF_E_NOMEM;
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counters, NUM_COUNTER_SLOTS * sizeof(unsigned long long));
+    if (e == cudaSuccess) {
+        bdf::crc_tables_init_kernel<<<1, 256, 0, ctx->stream>>>();
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+    if (e != cudaSuccess) {
+        fprintf(stderr, "bdf_ctx_create: %s\n", cudaGetErrorString(e));
+        bdf_ctx_destroy(ctx);
+        return BDF_E_CUDA;
+    }
+    *out = ctx;
+    return BDF_E_OK;
+}
+
+void bdf_ctx_destroy(bdf_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->in, &ctx->out, &ctx->in_off, &ctx->out_off, &ctx->max_out,
+                      &ctx->out_size, &ctx->status, &ctx->checksum};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    bdf::deflate_scratch_free(ctx->deflate_scratch);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *bdf_last_error(const bdf_ctx *ctx) { return ctx ? ctx->err : "null ctx"; }
+uint64_t bdf_kernel_launches(const bdf_ctx *ctx) { return ctx ? ctx->launches : 0; }
+float bdf_last_kernel_ms(const bdf_ctx *ctx) { return ctx ? ctx->last_ms : 0.f; }
+
+void *bdf_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void bdf_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+size_t bdf_compress_bound(int format, size_t len)
+{
+    size_t b = len + (len / 65535 + 1) * 5 + 10;
+    return b + (format == BDF_ZLIB ? 6 : format == BDF_GZIP ? 18 : 0);
+}
+
+// ---------------------------------------------------------------- decompress
+static int decompress_device_locked(bdf_ctx *ctx, int format, const uint8_t *in, const uint64_t *in_off,
+                                    size_t n, uint8_t *out, const uint64_t *out_off, const uint64_t *max_out,
+                                    uint64_t *out_size, uint32_t *checksum, int32_t *status, cudaStream_t s)
+{
+    if (n == 0) return BDF_E_OK;
+    if (n > 0xFFFFFFF0ull) return fail(ctx, BDF_E_ARG, "too many streams");
+    bdf::InflateArgs a;
+    a.in = in; a.in_off = in_off; a.out = out; a.out_off = out_off; a.max_out = max_out;
+    a.out_size = out_size; a.checksum = checksum; a.status = status; a.n = (uint32_t)n;
+    a.work_counter = next_counter(ctx, s);
+    switch (format) {
+        case BDF_RAW: return launch_inflate<BDF_RAW>(ctx, a, s);
+        case BDF_ZLIB: return launch_inflate<BDF_ZLIB>(ctx, a, s);
+        default: return launch_inflate<BDF_GZIP>(ctx, a, s);
+    }
+}
+
+int bdf_decompress_batch_device(bdf_ctx *ctx, int format, const uint8_t *in, const uint64_t *in_off, size_t n,
+                                uint8_t *out, const uint64_t *out_off, const uint64_t *max_out,
+                                uint64_t *out_size, uint32_t *checksum, int32_t *status, void *stream)
+{
+    if (!ctx) return BDF_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (bad_format(format)) return fail(ctx, BDF_E_ARG, "unknown format");
+    if (n && (!in || !in_off || !out || !out_off || !max_out || !out_size || !status))
+        return fail(ctx, BDF_E_ARG, "null pointer");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    return decompress_device_locked(ctx, format, in, in_off, n, out, out_off, max_out, out_size, checksum,
+                                    status, s);
+}
+
+int bdf_decompress_batch_host(bdf_ctx *ctx, int format, const uint8_t *in, const uint64_t *in_off, size_t n,
+                              uint8_t *out, const uint64_t *out_off, const uint64_t *max_out,
+                              uint64_t *out_size, uint32_t *checksum, int32_t *status)
+{
+    if (!ctx) return BDF_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (bad_format(format)) return fail(ctx, BDF_E_ARG, "unknown format");
+    if (n == 0) return BDF_E_OK;
+    if (!in || !in_off || !out || !out_off || !max_out || !out_size || !status)
+        return fail(ctx, BDF_E_ARG, "null pointer");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t in_bytes = (size_t)in_off[n];
+    size_t out_bytes = 0;
+    for (size_t i = 0; i < n; i++) {
+        size_t e = (size_t)(out_off[i] + max_out[i]);
+        if (e > out_bytes) out_bytes = e;
+    }
+    int rc;
+    if ((rc = ensure(ctx, ctx->in, in_bytes + 8)) || (rc = ensure(ctx, ctx->out, out_bytes + 8)) ||
+        (rc = ensure(ctx, ctx->in_off, (n + 1) * 8)) || (rc = ensure(ctx, ctx->out_off, n * 8)) ||
+        (rc = ensure(ctx, ctx->max_out, n * 8)) || (rc = ensure(ctx, ctx->out_size, n * 8)) ||
+        (rc = ensure(ctx, ctx->status, n * 4)) || (rc = ensure(ctx, ctx->checksum, n * 4)))
+        return rc;
+    CK(cudaMemcpyAsync(ctx->in.p, in, in_bytes, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->in_off.p, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->out_off.p, out_off, n * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->max_out.p, max_out, n * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(ctx->ev0, s));
+    rc = decompress_device_locked(ctx, format, (const uint8_t *)ctx->in.p, (const uint64_t *)ctx->in_off.p, n,
+                                  (uint8_t *)ctx->out.p, (const uint64_t *)ctx->out_off.p,
+                                  (const uint64_t *)ctx->max_out.p, (uint64_t *)ctx->out_size.p,
+                                  (uint32_t *)ctx->checksum.p, (int32_t *)ctx->status.p, s);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev1, s));
+    CK(cudaMemcpyAsync(out_size, ctx->out_size.p, n * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(status, ctx->status.p, n * 4, cudaMemcpyDeviceToHost, s));
+    if (checksum) CK(cudaMemcpyAsync(checksum, ctx->checksum.p, n * 4, cudaMemcpyDeviceToHost, s));
+    if (out_bytes) CK(cudaMemcpyAsync(out, ctx->out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    return BDF_E_OK;
+}
+
+// ------------------------------------------------------------------ compress
+int bdf_compress_batch_device(bdf_ctx *ctx, int level, int format, const uint8_t *in, const uint64_t *in_off,
+                              size_t n, uint8_t *out, const uint64_t *out_off, uint64_t *out_size,
+                              int32_t *status, void *stream)
+{
+    if (!ctx) return BDF_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (bad_format(format)) return fail(ctx, BDF_E_ARG, "unknown format");
+    if (level < 0) return fail(ctx, BDF_E_ARG, "negative level");
+    if (n == 0) return BDF_E_OK;
+    if (!in || !in_off || !out || !out_off || !out_size || !status) return fail(ctx, BDF_E_ARG, "null pointer");
+    if (n > 0xFFFFFFF0ull) return fail(ctx, BDF_E_ARG, "too many streams");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    bdf::DeflateArgs a;
+    a.in = in; a.in_off = in_off; a.out = out; a.out_off = out_off; a.out_size = out_size; a.status = status;
+    a.n = (uint32_t)n; a.level = level > 12 ? 12 : level; a.format = format;
+    a.work_counter = next_counter(ctx, s);
+    int nl = 0;
+    const char *why = nullptr;
+    cudaError_t e = bdf::launch_deflate(a, ctx->deflate_scratch, ctx->sm_count, s, &nl, &why);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail(ctx, BDF_E_CUDA, why ? why : "launch_deflate", e);
+    if (why) return fail(ctx, BDF_E_UNSUPPORTED, why);
+    return BDF_E_OK;
+}
+
+int bdf_compress_batch_host(bdf_ctx *ctx, int level, int format, const uint8_t *in, const uint64_t *in_off,
+                            size_t n, uint8_t *out, const uint64_t *out_off, uint64_t *out_size, int32_t *status)
+{
+    if (!ctx) return BDF_E_ARG;
+    if (bad_format(format)) return fail(ctx, BDF_E_ARG, "unknown format");
+    if (n == 0) return BDF_E_OK;
+    if (!in || !in_off || !out || !out_off || !out_size || !status) return fail(ctx, BDF_E_ARG, "null pointer");
+    size_t in_bytes, out_bytes = 0;
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        CK(cudaSetDevice(ctx->device));
+        in_bytes = (size_t)in_off[n];
+        for (size_t i = 0; i < n; i++) {
+            size_t e = (size_t)out_off[i] + bdf_compress_bound(format, (size_t)(in_off[i + 1] - in_off[i]));
+            if (e > out_bytes) out_bytes = e;
+        }
+        int rc;
+        if ((rc = ensure(ctx, ctx->in, in_bytes + 8)) || (rc = ensure(ctx, ctx->out, out_bytes + 8)) ||
+            (rc = ensure(ctx, ctx->in_off, (n + 1) * 8)) || (rc = ensure(ctx, ctx->out_off, n * 8)) ||
+            (rc = ensure(ctx, ctx->out_size, n * 8)) || (rc = ensure(ctx, ctx->status, n * 4)))
+            return rc;
+        cudaStream_t s = ctx->stream;
+        CK(cudaMemcpyAsync(ctx->in.p, in, in_bytes, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->in_off.p, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->out_off.p, out_off, n * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaEventRecord(ctx->ev0, s));
+    }
+    int rc = bdf_compress_batch_device(ctx, level, format, (const uint8_t *)ctx->in.p,
+                                       (const uint64_t *)ctx->in_off.p, n, (uint8_t *)ctx->out.p,
+                                       (const uint64_t *)ctx->out_off.p, (uint64_t *)ctx->out_size.p,
+                                       (int32_t *)ctx->status.p, nullptr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaStream_t s = ctx->stream;
+    CK(cudaEventRecord(ctx->ev1, s));
+    CK(cudaMemcpyAsync(out_size, ctx->out_size.p, n * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(status, ctx->status.p, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    // Copy back only what was produced: contiguous runs of streams are merged
+    // so that a 4 GiB bound-sized slab is not dragged over PCIe for a few MB.
+    size_t i = 0;
+    while (i < n) {
+        size_t beg = (size_t)out_off[i], end = beg + (size_t)out_size[i];
+        size_t j = i + 1;
+        // merge neighbours whose gap is small (cheaper than another copy call)
+        while (j < n && (size_t)out_off[j] >= end && (size_t)out_off[j] - end <= 4096) {
+            end = (size_t)out_off[j] + (size_t)out_size[j];
+            j++;
+        }
+        if (end > beg) CK(cudaMemcpyAsync(out + beg, (const uint8_t *)ctx->out.p + beg, end - beg,
+                                          cudaMemcpyDeviceToHost, s));
+        i = j;
+    }
+    CK(cudaStreamSynchronize(s));
+    return BDF_E_OK;
+}
+
+// ------------------------------------------------------------------ checksum
+int bdf_checksum_batch_device(bdf_ctx *ctx, int kind, const uint8_t *in, const uint64_t *in_off, size_t n,
+                              uint32_t *out, void *stream)
+{
+    if (!ctx) return BDF_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (kind != BDF_ADLER32 && kind != BDF_CRC32) return fail(ctx, BDF_E_ARG, "unknown checksum kind");
+    if (n == 0) return BDF_E_OK;
+    if (!in || !in_off || !out) return fail(ctx, BDF_E_ARG, "null pointer");
+    if (n > 0xFFFFFFF0ull) return fail(ctx, BDF_E_ARG, "too many streams");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    bdf::ChecksumArgs a{in, in_off, out, (uint32_t)n};
+    unsigned long long want = (n + bdf::CK_WARPS_PER_BLOCK - 1) / bdf::CK_WARPS_PER_BLOCK;
+    unsigned long long full = (unsigned long long)ctx->sm_count * 8;
+    unsigned grid = (unsigned)(want < full ? want : full);
+    if (kind == BDF_CRC32)
+        bdf::checksum_kernel<BDF_CRC32><<<grid, bdf::CK_WARPS_PER_BLOCK * 32, 0, s>>>(a);
+    else
+        bdf::checksum_kernel<BDF_ADLER32><<<grid, bdf::CK_WARPS_PER_BLOCK * 32, 0, s>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return BDF_E_OK;
+}
+
+int bdf_checksum_batch_host(bdf_ctx *ctx, int kind, const uint8_t *in, const uint64_t *in_off, size_t n,
+                            uint32_t *out)
+{
+    if (!ctx) return BDF_E_ARG;
+    if (n == 0) return BDF_E_OK;
+    if (!in || !in_off || !out) return fail(ctx, BDF_E_ARG, "null pointer");
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        CK(cudaSetDevice(ctx->device));
+        int rc;
+        if ((rc = ensure(ctx, ctx->in, (size_t)in_off[n] + 8)) || (rc = ensure(ctx, ctx->in_off, (n + 1) * 8)) ||
+            (rc = ensure(ctx, ctx->checksum, n * 4)))
+            return rc;
+        CK(cudaMemcpyAsync(ctx->in.p, in, (size_t)in_off[n], cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->in_off.p, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    }
+    int rc = bdf_checksum_batch_device(ctx, kind, (const uint8_t *)ctx->in.p, (const uint64_t *)ctx->in_off.p, n,
+                                       (uint32_t *)ctx->checksum.p, nullptr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaMemcpyAsync(out, ctx->checksum.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    return BDF_E_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// common.cuh — shared device helpers for the batch DEFLATE kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/bdeflate.h"
+
+#define BDF_FULL_MASK 0xFFFFFFFFu
+
+namespace bdf {
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// RFC 1951 length / offset code geometry, computed instead of tabulated so
+// that divergent lanes never serialise on constant memory.
+__device__ __forceinline__ void length_slot_info(unsigned slot, unsigned &base, unsigned &extra)
+{
+    if (slot < 8) { base = 3 + slot; extra = 0; }
+    else if (slot >= 28) { base = 258; extra = 0; }   // 286/287 decode as 258 (tables.rs:342-343)
+    else { extra = (slot >> 2) - 1; base = ((4 + (slot & 3)) << extra) + 3; }
+}
+__device__ __forceinline__ void offset_slot_info(unsigned slot, unsigned &base, unsigned &extra)
+{
+    if (slot > 29) slot = 29;                          // 30/31 alias 29 (tables.rs:377-378)
+    if (slot < 4) { base = slot + 1; extra = 0; }
+    else { extra = (slot >> 1) - 1; base = ((2 + (slot & 1)) << extra) + 1; }
+}
+
+// ---- CRC-32 (reflected 0xEDB88320) in GF(2): no CLMUL on sm_100, so streams
+// are split across lanes and the partial CRCs are recombined with x^(8k) mod P
+// multipliers — the GF(2) analogue of the fold constants the reference keeps
+// in src/crc32_tables.rs:36-49.
+#define BDF_CRC_POLY 0xEDB88320u
+__device__ __forceinline__ uint32_t gf2_mulmod(uint32_t a, uint32_t b)
+{
+    uint32_t p = 0;
+#pragma unroll 1
+    for (int i = 0; i < 32; i++) {
+        p ^= b & (0u - (a >> 31));
+        a <<= 1;
+        b = (b >> 1) ^ (BDF_CRC_POLY & (0u - (b & 1u)));
+    }
+    return p;
+}
+// x^(8*nbytes) mod P; x2n[k] = x^(2^k) mod P lives in shared or constant memory.
+__device__ __forceinline__ uint32_t gf2_xpow8n(uint64_t nbytes, const uint32_t *x2n)
+{
+    uint32_t p = 0x80000000u;  // x^0
+    unsigned k = 3;
+    while (nbytes) {
+        if (nbytes & 1) p = gf2_mulmod(x2n[k & 31], p);
+        nbytes >>= 1;
+        k++;
+    }
+    return p;
+}
+
+struct CrcTables {
+    uint32_t slice[4][256];  // slice-by-4
+    uint32_t x2n[32];
+};
+__device__ CrcTables g_crc_tables;            // single translation unit (bdeflate.cu); filled by crc_tables_init_kernel
+
+}  // namespace bdf
