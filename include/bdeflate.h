@@ -92,8 +92,9 @@ size_t bdf_compress_bound(int format, size_t len);
  * Like the reference, trailing input after the final block is ignored and
  * producing fewer than max_out[i] bytes is success.
  * *_device: every pointer is device memory valid on the ctx's device; the
- * work is enqueued on `stream` (a cudaStream_t, NULL = the ctx stream) and
- * the call returns without synchronising.  *_host: every pointer is host
+ * work is enqueued on `stream` (a cudaStream_t; NULL means the ctx's own
+ * stream — pass cudaStreamLegacy / cudaStreamPerThread explicitly to target
+ * the default streams) and the call returns without synchronising.  *_host: every pointer is host
  * memory; the call copies in, runs, copies out and returns when the results
  * are in place.
  */

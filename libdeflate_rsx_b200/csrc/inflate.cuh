@@ -271,34 +271,144 @@ __device__ __forceinline__ void flush_literals(OutState &o, unsigned lane)
     }
 }
 
+// ---- match copy ------------------------------------------------------------
 // out[pos+i] = out[pos-offset+i], i < length, with the period-replication rule
 // for offset < length (src/decompress/mod.rs:1259-1317, x86.rs copy_match_bmi2).
+// The warp moves 8 destination-aligned bytes per lane per round: the source run
+// is fetched as aligned 32-bit words and realigned with PRMT, so a 258-byte
+// match is two rounds of LDG/PRMT/STG.64 instead of 258 byte moves, and the
+// Adler-32 partial sums advance 8 bytes at a time with dp4a.
+template <bool ADLER>
+__device__ __forceinline__ void adler_acc8(OutState &o, uint32_t idx, uint32_t x, uint32_t y)
+{
+    if (ADLER) {
+        uint32_t s = __dp4a(x, 0x01010101u, __dp4a(y, 0x01010101u, 0u));
+        uint32_t w = __dp4a(x, 0x03020100u, __dp4a(y, 0x07060504u, 0u));
+        o.sumA += s;
+        o.sumB += (uint64_t)idx * s + w;
+    }
+}
+template <bool ADLER>
+__device__ __forceinline__ void adler_acc1(OutState &o, uint32_t idx, uint32_t b)
+{
+    if (ADLER) { o.sumA += b; o.sumB += (uint64_t)idx * b; }
+}
+
+// Splits [dpos, dpos+n) into head bytes (to 8-byte alignment), 8-byte words, tail bytes.
+struct CopySplit { uint32_t head, nbody, tail; };
+__device__ __forceinline__ CopySplit split_dst(const uint8_t *base, uint32_t dpos, uint32_t n)
+{
+    CopySplit c;
+    c.head = (uint32_t)((8u - (uint32_t)(reinterpret_cast<uintptr_t>(base + dpos) & 7u)) & 7u);
+    if (c.head > n) c.head = n;
+    c.nbody = (n - c.head) >> 3;
+    c.tail = (n - c.head) & 7u;
+    return c;
+}
+// byte index (relative to dpos) this lane moves in the head/tail round, or ~0u
+__device__ __forceinline__ uint32_t edge_index(const CopySplit &c, unsigned lane)
+{
+    if (lane < c.head) return lane;
+    if (lane >= 8 && lane - 8 < c.tail) return c.head + c.nbody * 8 + (lane - 8);
+    return 0xFFFFFFFFu;
+}
+
+// Non-overlapping forward copy inside the output buffer: out[dpos..dpos+n) = out[spos..spos+n),
+// spos + n <= dpos.
+template <bool ADLER>
+__device__ __forceinline__ void warp_copy_fwd(OutState &o, unsigned lane, uint32_t dpos, uint32_t spos, uint32_t n)
+{
+    uint8_t *base = o.out;
+    const CopySplit c = split_dst(base, dpos, n);
+    const uint32_t ei = edge_index(c, lane);
+    if (ei != 0xFFFFFFFFu) {
+        uint32_t b = base[spos + ei];
+        base[dpos + ei] = (uint8_t)b;
+        adler_acc1<ADLER>(o, dpos + ei, b);
+    }
+    for (uint32_t w = lane; w < c.nbody; w += 32) {
+        const uint32_t rel = c.head + 8 * w;
+        const uint8_t *sp = base + spos + rel;
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(sp) & 3u);
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(sp - sh);
+        uint32_t w0 = sw[0], w1 = sw[1], w2 = sh ? sw[2] : 0u;
+        const uint32_t sel = 0x3210u + 0x1111u * sh;
+        uint32_t x = __byte_perm(w0, w1, sel), y = __byte_perm(w1, w2, sel);
+        *reinterpret_cast<uint2 *>(base + dpos + rel) = make_uint2(x, y);
+        adler_acc8<ADLER>(o, dpos + rel, x, y);
+    }
+}
+
+// Overlapping copy with a short period (2 <= offset < 32, offset < length): every lane
+// builds its 8 bytes from the period directly.
+template <bool ADLER>
+__device__ __forceinline__ void warp_copy_period(OutState &o, unsigned lane, uint32_t dpos, uint32_t offset,
+                                                 uint32_t n)
+{
+    uint8_t *base = o.out;
+    const uint8_t *pat = base + dpos - offset;
+    const CopySplit c = split_dst(base, dpos, n);
+    const uint32_t ei = edge_index(c, lane);
+    if (ei != 0xFFFFFFFFu) {
+        uint32_t b = pat[ei % offset];
+        base[dpos + ei] = (uint8_t)b;
+        adler_acc1<ADLER>(o, dpos + ei, b);
+    }
+    for (uint32_t w = lane; w < c.nbody; w += 32) {
+        const uint32_t rel = c.head + 8 * w;
+        uint32_t j = rel % offset;
+        uint32_t v[2] = {0, 0};
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            v[k >> 2] |= (uint32_t)pat[j] << (8 * (k & 3));
+            j = j + 1 == offset ? 0 : j + 1;
+        }
+        *reinterpret_cast<uint2 *>(base + dpos + rel) = make_uint2(v[0], v[1]);
+        adler_acc8<ADLER>(o, dpos + rel, v[0], v[1]);
+    }
+}
+
+// Run of one byte (offset == 1).
+template <bool ADLER>
+__device__ __forceinline__ void warp_fill(OutState &o, unsigned lane, uint32_t dpos, uint32_t n)
+{
+    uint8_t *base = o.out;
+    const uint32_t b = base[dpos - 1];
+    const uint32_t word = b * 0x01010101u;
+    const CopySplit c = split_dst(base, dpos, n);
+    const uint32_t ei = edge_index(c, lane);
+    if (ei != 0xFFFFFFFFu) {
+        base[dpos + ei] = (uint8_t)b;
+        adler_acc1<ADLER>(o, dpos + ei, b);
+    }
+    for (uint32_t w = lane; w < c.nbody; w += 32) {
+        const uint32_t rel = c.head + 8 * w;
+        *reinterpret_cast<uint2 *>(base + dpos + rel) = make_uint2(word, word);
+        adler_acc8<ADLER>(o, dpos + rel, word, word);
+    }
+}
+
 template <bool ADLER>
 __device__ __forceinline__ void copy_match(OutState &o, unsigned lane, unsigned length, unsigned offset)
 {
     __syncwarp();   // earlier stores by other lanes may be our source
-    const uint8_t *src = o.out + (o.pos - offset);
-    uint8_t *dst = o.out + o.pos;
-    unsigned j = lane, step = 32;
-    if (offset < 32) {          // only then can a lane index reach past one period
-        j = lane % offset;
-        step = 32 % offset;
-    }
-    const bool wrap = offset < length;
-    uint8_t v[9];
-#pragma unroll
-    for (int k = 0; k < 9; k++) {
-        unsigned i = lane + 32 * k;
-        if (i < length) v[k] = src[wrap ? j : i];
-        j += step;
-        if (j >= offset) j -= offset;
-    }
-#pragma unroll
-    for (int k = 0; k < 9; k++) {
-        unsigned i = lane + 32 * k;
-        if (i < length) {
-            dst[i] = v[k];
-            if (ADLER) { o.sumA += v[k]; o.sumB += (uint64_t)(o.pos + i) * v[k]; }
+    if (offset >= length) {
+        warp_copy_fwd<ADLER>(o, lane, o.pos, o.pos - offset, length);
+    } else if (offset == 1) {
+        warp_fill<ADLER>(o, lane, o.pos, length);
+    } else if (offset < 32) {
+        warp_copy_period<ADLER>(o, lane, o.pos, offset, length);
+    } else {
+        // period >= 32: each pass copies everything that is already periodic
+        // ([pos-offset, pos+done) holds 1 + done/offset periods), doubling per pass
+        uint32_t done = 0;
+        for (;;) {
+            uint32_t n = offset + done;
+            if (n > length - done) n = length - done;
+            warp_copy_fwd<ADLER>(o, lane, o.pos + done, o.pos - offset, n);
+            done += n;
+            if (done >= length) break;
+            __syncwarp();
         }
     }
     o.pos += length;
@@ -539,7 +649,7 @@ struct InflateArgs {
 };
 
 template <int FORMAT>
-__global__ void __launch_bounds__(INF_WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(INF_WARPS_PER_BLOCK * 32, 8)
 inflate_kernel(InflateArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -121,13 +121,14 @@ def compress_batch(flat, in_off, level, fmt=RAW, nthreads=0):
     return out, out_off, out_size, status
 
 
-def decompress_batch(flat, in_off, max_out, fmt=RAW, nthreads=0):
+def decompress_batch(flat, in_off, max_out, fmt=RAW, nthreads=0, out=None):
     n = len(in_off) - 1
     max_out = np.asarray(max_out, dtype=np.uint64)
     out_off = np.zeros(n, dtype=np.uint64)
     if n:
         out_off[1:] = np.cumsum(max_out)[:-1]
-    out = np.zeros(int(max_out.sum()) + 1, dtype=np.uint8)
+    if out is None:
+        out = np.zeros(int(max_out.sum()) + 1, dtype=np.uint8)
     out_size = np.zeros(n, dtype=np.uint64)
     status = np.zeros(n, dtype=np.int32)
     lib().orc_decompress_batch(fmt, _ptr(flat), _ptr(in_off), n, _ptr(out), _ptr(out_off),

@@ -1,0 +1,94 @@
+"""GPU parity tests: batch checksums and batch compression through the C ABI."""
+import zlib
+
+import numpy as np
+import pytest
+
+import corpus
+import kats
+import oracle_lib as o
+
+pytestmark = pytest.mark.gpu
+K = kats.load()
+WBITS = {0: -15, 1: 15, 2: 31}
+
+
+def inputs():
+    return corpus.small_cases() + [
+        corpus.corpus_a_stream(0), corpus.corpus_a_stream(11), corpus.text_stream(1),
+        corpus.binary_stream(2), corpus.lowentropy_stream(3), corpus.offset_stream(3),
+        corpus.offset_stream(32), corpus.text_stream(6, 70000),
+        np.random.default_rng(5).integers(0, 256, 4000, dtype=np.uint8).tobytes(),
+    ]
+
+
+def test_checksum_reference_kats(engine):
+    data = [d for d, _, _ in K["adler32"]]
+    assert engine.checksum_batch(data, engine.ADLER32) == [e for _, e, _ in K["adler32"]]
+    data = [d for d, _, _ in K["crc32"]]
+    assert engine.checksum_batch(data, engine.CRC32) == [e for _, e, _ in K["crc32"]]
+
+
+def test_checksum_tails_alignment_and_overflow(engine):
+    bufs = [bytes(i % 255 for i in range(n)) for n in K["crc_tail_sizes"]]
+    bufs += [b"\xff" * 100000, b"\xff" * 1000000, corpus.text_stream(3, 65537)]
+    # misaligned starts inside the flat buffer come for free: sizes are odd
+    for kind, ref in ((engine.ADLER32, zlib.adler32), (engine.CRC32, zlib.crc32)):
+        assert engine.checksum_batch(bufs, kind) == [ref(b) for b in bufs]
+        flat, off = o.flatten(bufs)
+        assert engine.checksum_batch(bufs, kind) == [int(x) for x in o.checksum_batch(flat, off, kind)]
+    assert engine.checksum_batch([], engine.CRC32) == []
+
+
+def levels_implemented(engine):
+    out = []
+    for level in range(0, 13):
+        try:
+            engine.BatchCompressor(level).compress_batch([b"probe"])
+            out.append(level)
+        except engine.BdfError as e:
+            assert "not implemented" in str(e)
+    return out
+
+
+def test_compress_byte_identical_to_oracle(engine):
+    """Levels 0..9: byte-identical to the oracle (the repository's definition of
+    the reference's output); every stream also inflates under system zlib."""
+    lv = [l for l in levels_implemented(engine) if l <= 9]
+    assert 0 in lv
+    for fmt in (0, 1, 2):
+        for level in lv:
+            got = engine.BatchCompressor(level, format=fmt).compress_batch(inputs())
+            for g, s in zip(got, inputs()):
+                exp = o.compress(s, level, fmt)
+                assert g == (exp if exp is not None else b""), (fmt, level, len(s))
+                if exp is not None and not (level == 0 and len(s) == 0):
+                    assert zlib.decompress(g, WBITS[fmt]) == s
+
+
+def test_compress_failure_is_in_band(engine):
+    # incompressible input: empty result, not an exception and not a stored block (src/batch.rs:52-53)
+    rnd = np.random.default_rng(0).integers(0, 256, 65536, dtype=np.uint8).tobytes()
+    for level in [l for l in levels_implemented(engine) if l >= 1]:
+        got = engine.BatchCompressor(level).compress_batch([rnd, b"abcabcabcabc" * 10])
+        assert got[0] == b"" and got[1] == o.compress(b"abcabcabcabc" * 10, level)
+    assert engine.BatchCompressor(0).compress_batch([]) == []
+
+
+def test_compress_ratio_tier(engine):
+    """Levels 10..12: total compressed size within 0.5 % of the oracle's, and
+    every stream round-trips through zlib."""
+    lv = [l for l in levels_implemented(engine) if l >= 10]
+    if not lv:
+        pytest.skip("levels 10-12 not implemented in this round")
+    ins = [s for s in inputs() if len(s) >= 1000]
+    for level in lv:
+        got = engine.BatchCompressor(level).compress_batch(ins)
+        tot_g = tot_o = 0
+        for g, s in zip(got, ins):
+            exp = o.compress(s, level)
+            if exp is None:
+                continue
+            assert zlib.decompress(g, -15) == s
+            tot_g += len(g); tot_o += len(exp)
+        assert tot_g <= tot_o * 1.005, (level, tot_g, tot_o)
