@@ -43,7 +43,8 @@ enum bdf_status {
     BDF_BAD_DATA = 1,
     BDF_SHORT_OUTPUT = 2, /* declared by the reference, never produced */
     BDF_INSUFFICIENT_SPACE = 3,
-    BDF_SHORT_INPUT = 4
+    BDF_SHORT_INPUT = 4,
+    BDF_STREAM_UNSUPPORTED = 100 /* not a reference status: outside this build's range */
 };
 
 /* Call-level errors. */
@@ -116,6 +117,10 @@ int bdf_decompress_batch_host(bdf_ctx *ctx, int format, const uint8_t *in,
  * out + out_off[i]; a stream whose encoding does not fit fails with
  * BDF_INSUFFICIENT_SPACE and out_size[i] = 0 — the reference has no
  * stored-block fallback (src/compress/mod.rs:641-644).
+ * Limits of this build: levels 10..12 return BDF_E_UNSUPPORTED; at levels >= 1
+ * a stream longer than 65536 bytes is not compressed — the *_host call returns
+ * BDF_E_UNSUPPORTED before doing any work, the *_device call (which cannot see
+ * the lengths) sets status[i] = BDF_STREAM_UNSUPPORTED for that stream.
  */
 int bdf_compress_batch_device(bdf_ctx *ctx, int level, int format,
                               const uint8_t *in, const uint64_t *in_off, size_t n,

@@ -1,0 +1,316 @@
+// deflate_common.cuh — pieces shared by the compression kernels (sm_100a):
+// framing, the warp bit sink (prefix-sum bit packer), cooperative match length,
+// RFC 1951 symbol geometry, and the length-limited Huffman code builder.
+#pragma once
+#include "checksum.cuh"
+#include "common.cuh"
+
+namespace bdf {
+
+
+struct DeflateArgs {
+    const uint8_t *in;
+    const uint64_t *in_off;
+    uint8_t *out;
+    const uint64_t *out_off;
+    uint64_t *out_size;
+    int32_t *status;
+    unsigned long long *work_counter;
+    void *scratch;           // per-CTA scratch slabs (levels 2..9)
+    uint64_t scratch_stride; // bytes per CTA
+    uint32_t n;
+    int level;
+    int format;
+};
+
+__host__ __device__ inline uint64_t deflate_bound(uint64_t len) { return len + (len / 65535 + 1) * 5 + 10; }
+
+// ---- framing (compress_zlib / compress_gzip, src/compress/mod.rs:2248-2357); warp-uniform
+__device__ __forceinline__ unsigned frame_header(int format, int level, uint8_t *out, unsigned lane)
+{
+    if (format == BDF_ZLIB) {
+        unsigned hint = level < 2 ? 0 : level < 6 ? 1 : level < 8 ? 2 : 3;
+        unsigned hdr = (8u << 8) | (7u << 12) | (hint << 6);
+        hdr |= 31 - (hdr % 31);
+        if (lane == 0) { out[0] = (uint8_t)(hdr >> 8); out[1] = (uint8_t)hdr; }
+        return 2;
+    }
+    if (format == BDF_GZIP) {
+        if (lane < 10) {
+            uint8_t b = 0;
+            if (lane == 0) b = 0x1F;
+            else if (lane == 1) b = 0x8B;
+            else if (lane == 2) b = 8;
+            else if (lane == 8) b = level < 2 ? 4 : level >= 8 ? 2 : 0;
+            else if (lane == 9) b = 255;
+            out[lane] = b;
+        }
+        return 10;
+    }
+    return 0;
+}
+// Writes the footer after `at` bytes; returns the framed size.  One warp.
+__device__ __forceinline__ uint64_t frame_footer(int format, const uint8_t *in, uint64_t len, uint8_t *out,
+                                                 uint64_t at, const uint32_t (*s_crc)[256],
+                                                 const uint32_t *s_x2n, unsigned lane)
+{
+    if (format == BDF_ZLIB) {
+        uint32_t a = warp_adler32(in, len, lane);
+        if (lane < 4) out[at + lane] = (uint8_t)(a >> (24 - 8 * lane));     // big-endian
+        return at + 4;
+    }
+    if (format == BDF_GZIP) {
+        uint32_t c = warp_crc32(in, len, s_crc, s_x2n, lane);
+        uint32_t isz = (uint32_t)len;
+        if (lane < 4) out[at + lane] = (uint8_t)(c >> (8 * lane));
+        else if (lane < 8) out[at + lane] = (uint8_t)(isz >> (8 * (lane - 4)));
+        return at + 8;
+    }
+    return at;
+}
+__device__ __forceinline__ void load_crc_tables_to_smem(uint32_t (*s_crc)[256], uint32_t *s_x2n)
+{
+    for (unsigned i = threadIdx.x; i < 1024; i += blockDim.x) s_crc[i >> 8][i & 255] = g_crc_tables.slice[i >> 8][i & 255];
+    if (threadIdx.x < 32) s_x2n[threadIdx.x] = g_crc_tables.x2n[threadIdx.x];
+    __syncthreads();
+}
+
+// ---- symbol geometry
+__device__ __forceinline__ unsigned length_slot_of(unsigned len)      // LENGTH_WRITE_TABLE[len] >> 24
+{
+    if (len <= 10) return len - 3;
+    if (len == 258) return 28;
+    unsigned v = len - 3;
+    unsigned l = 31u - __clz(v);           // >= 3
+    return 4 * (l - 1) + ((v >> (l - 2)) & 3u);
+}
+__device__ __forceinline__ unsigned offset_slot_of(unsigned off)      // get_offset_slot, src/compress/mod.rs:2197-2207
+{
+    if (off <= 2) return off - 1;
+    unsigned v = off - 1;
+    unsigned l = 31u - __clz(v);
+    return 2 * l + ((v >> (l - 1)) & 1u);
+}
+__device__ __forceinline__ uint32_t ld24(const uint8_t *p)
+{
+    return p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16;
+}
+__device__ __forceinline__ uint32_t hash3(uint32_t v24) { return (v24 * 0x1E35A7BDu) >> 17; }
+
+// ---- warp bit sink: LSB-first bit stream (Bitstream, src/compress/bitstream.rs).
+// Every lane contributes (bits, n <= 32) in lane order; bit offsets come from a
+// warp inclusive scan, bits are OR-ed into a zeroed shared staging buffer, and
+// whole words are flushed to global memory.  Capacity is enforced the way the
+// reference's checked writes do: the stream fails as soon as a completed byte
+// does not fit (bitstream.rs:143-189,194-222).
+constexpr uint32_t SINK_WORDS = 512;                 // 2 KiB staging per sink
+constexpr uint32_t SINK_FLUSH_BITS = 8192;           // flush once 1 KiB is pending
+
+struct BitSink {
+    uint32_t *buf;      // shared, SINK_WORDS, zero-filled outside [0, nbits)
+    uint8_t *out;       // global destination
+    uint64_t cap;       // bytes available at out
+    uint64_t flushed;   // bytes already stored
+    uint32_t nbits;     // bits pending in buf
+    bool overflow;
+
+    __device__ __forceinline__ void init(uint32_t *staging, uint8_t *dst, uint64_t capacity, unsigned lane)
+    {
+        buf = staging; out = dst; cap = capacity; flushed = 0; nbits = 0; overflow = false;
+        for (unsigned i = lane; i < SINK_WORDS; i += 32) buf[i] = 0;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void flush_words(unsigned lane)
+    {
+        const uint32_t nfull = nbits >> 5;
+        const uint64_t bytes = (uint64_t)nfull * 4;
+        __syncwarp();
+        if (flushed + bytes > cap) overflow = true;
+        if (!overflow) {
+            for (uint32_t w = lane; w < nfull; w += 32) {
+                uint32_t v = buf[w];
+                uint8_t *d = out + flushed + 4ull * w;
+                d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16); d[3] = (uint8_t)(v >> 24);
+            }
+        }
+        const uint32_t rem = buf[nfull];
+        __syncwarp();
+        for (uint32_t w = lane; w <= nfull; w += 32) buf[w] = 0;
+        __syncwarp();
+        if (lane == 0) buf[0] = rem;
+        __syncwarp();
+        flushed += bytes;
+        nbits &= 31u;
+    }
+    // all 32 lanes call; lanes with n == 0 contribute nothing
+    __device__ __forceinline__ void put(uint32_t bits, uint32_t n, unsigned lane)
+    {
+        uint32_t incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(BDF_FULL_MASK, incl, d);
+            if (lane >= (unsigned)d) incl += t;
+        }
+        const uint32_t total = __shfl_sync(BDF_FULL_MASK, incl, 31);
+        if (n) {
+            const uint32_t at = nbits + incl - n;
+            const uint32_t w = at >> 5, sh = at & 31u;
+            atomicOr(&buf[w], bits << sh);
+            if (sh + n > 32) atomicOr(&buf[w + 1], bits >> (32 - sh));
+        }
+        nbits += total;
+        __syncwarp();
+        if (nbits >= SINK_FLUSH_BITS) flush_words(lane);
+    }
+    // single (bits, n) item from a warp-uniform caller
+    __device__ __forceinline__ void put1(uint32_t bits, uint32_t n, unsigned lane)
+    {
+        if (n == 0) return;
+        if (lane == 0) {
+            const uint32_t w = nbits >> 5, sh = nbits & 31u;
+            buf[w] |= bits << sh;
+            if (sh + n > 32) buf[w + 1] |= bits >> (32 - sh);
+        }
+        nbits += n;
+        __syncwarp();
+        if (nbits >= SINK_FLUSH_BITS) flush_words(lane);
+    }
+    // Bitstream::flush: zero-pad to a byte and store everything.  Returns total bytes or ~0 on overflow.
+    __device__ __forceinline__ uint64_t finish(unsigned lane)
+    {
+        __syncwarp();
+        const uint32_t bytes = (nbits + 7) >> 3;
+        if (flushed + bytes > cap) overflow = true;
+        if (!overflow) {
+            for (uint32_t b = lane; b < bytes; b += 32) out[flushed + b] = (uint8_t)(buf[b >> 2] >> (8 * (b & 3)));
+        }
+        __syncwarp();
+        return overflow ? ~0ull : flushed + bytes;
+    }
+};
+
+// Common-prefix length of a[0..maxlen) and b[0..maxlen), maxlen <= 258, all lanes cooperate
+// (every match_len_* variant of the reference, src/compress/matchfinder.rs:245-694).
+__device__ __forceinline__ unsigned warp_match_len(const uint8_t *a, const uint8_t *b, unsigned maxlen, unsigned lane)
+{
+    for (unsigned base = 0; base < maxlen; base += 256) {
+        const unsigned i0 = base + lane * 8;
+        unsigned cnt = 0;
+#pragma unroll
+        for (unsigned k = 0; k < 8; k++) {
+            unsigned idx = i0 + k;
+            if (cnt == k && idx < maxlen && a[idx] == b[idx]) cnt++;
+        }
+        const unsigned stop = __ballot_sync(BDF_FULL_MASK, cnt != 8);
+        if (stop) {
+            const unsigned first = __ffs(stop) - 1;
+            return base + first * 8 + __shfl_sync(BDF_FULL_MASK, cnt, first);
+        }
+    }
+    return maxlen;
+}
+
+// ---- length-limited canonical Huffman code (make_huffman_code and helpers,
+// src/compress/huffman_comp.rs:8-155).  Serial, run by one thread on shared
+// arrays: a[] (num_syms words, doubles as the codeword output), lens[], and
+// cnt[] (num_syms words of scratch).  Ties are broken exactly as in the
+// reference: counting sort on min(freq, n-1), last bucket ordered by the
+// packed (freq << 10 | sym) key.
+__device__ void make_huffman_code_serial(unsigned num_syms, unsigned max_len, const uint32_t *freqs,
+                                         uint8_t *lens, uint32_t *a, uint32_t *cnt)
+{
+    const uint32_t SYM_MASK = 1023u, FREQ_MASK = ~1023u;
+    for (unsigned i = 0; i < num_syms; i++) cnt[i] = 0;
+    for (unsigned s = 0; s < num_syms; s++) {
+        uint32_t f = freqs[s];
+        cnt[f < num_syms - 1 ? f : num_syms - 1]++;
+    }
+    uint32_t run = 0;
+    for (unsigned i = 1; i < num_syms; i++) {
+        uint32_t c = cnt[i];
+        cnt[i] = run;
+        run += c;
+    }
+    const unsigned used = run;
+    for (unsigned s = 0; s < num_syms; s++) {
+        uint32_t f = freqs[s];
+        if (f) {
+            unsigned b = f < num_syms - 1 ? f : num_syms - 1;
+            a[cnt[b]++] = s | (f << 10);
+        } else {
+            lens[s] = 0;
+        }
+    }
+    {   // order the overflow bucket by the packed key (insertion sort; keys are distinct)
+        const unsigned lo = cnt[num_syms - 2], hi = cnt[num_syms - 1];
+        for (unsigned i = lo + 1; i < hi; i++) {
+            uint32_t key = a[i];
+            unsigned j = i;
+            while (j > lo && a[j - 1] > key) { a[j] = a[j - 1]; j--; }
+            a[j] = key;
+        }
+    }
+    if (used < 2) {
+        unsigned sym = used ? (a[0] & SYM_MASK) : 0;
+        unsigned nz = sym ? sym : 1;
+        a[0] = 0; lens[0] = 1;
+        a[nz] = 1; lens[nz] = 1;
+        return;
+    }
+    {
+        const unsigned last = used - 1;
+        unsigned i = 0, b = 0, e = 0;
+        while (e < last) {
+            uint32_t nf;
+            if (i < last && (b == e || (a[i + 1] & FREQ_MASK) <= (a[b] & FREQ_MASK))) {
+                nf = (a[i] & FREQ_MASK) + (a[i + 1] & FREQ_MASK);
+                i += 2;
+            } else if (b + 2 <= e && (i > last || (a[b + 1] & FREQ_MASK) < (a[i] & FREQ_MASK))) {
+                nf = (a[b] & FREQ_MASK) + (a[b + 1] & FREQ_MASK);
+                a[b] = (e << 10) | (a[b] & SYM_MASK);
+                a[b + 1] = (e << 10) | (a[b + 1] & SYM_MASK);
+                b += 2;
+            } else {
+                nf = (a[i] & FREQ_MASK) + (a[b] & FREQ_MASK);
+                a[b] = (e << 10) | (a[b] & SYM_MASK);
+                i += 1;
+                b += 1;
+            }
+            a[e] = nf | (a[e] & SYM_MASK);
+            e++;
+        }
+    }
+    uint32_t len_counts[16];
+#pragma unroll
+    for (int l = 0; l < 16; l++) len_counts[l] = 0;
+    {
+        const unsigned root = used - 2;
+        len_counts[1] = 2;
+        a[root] &= SYM_MASK;
+        for (int node = (int)root - 1; node >= 0; node--) {
+            unsigned parent = a[node] >> 10;
+            unsigned depth = (a[parent] >> 10) + 1;
+            a[node] = (a[node] & SYM_MASK) | (depth << 10);
+            if (depth >= max_len) {
+                depth = max_len - 1;
+                while (len_counts[depth] == 0) depth--;
+            }
+            len_counts[depth]--;
+            len_counts[depth + 1] += 2;
+        }
+    }
+    {
+        unsigned i = 0;
+        for (unsigned len = max_len; len >= 1; len--)
+            for (uint32_t c = len_counts[len]; c > 0; c--) lens[a[i++] & SYM_MASK] = (uint8_t)len;
+        uint32_t next[16];
+        next[0] = 0; next[1] = 0;
+        for (unsigned len = 2; len <= max_len; len++) next[len] = (next[len - 1] + len_counts[len - 1]) << 1;
+        for (unsigned s = 0; s < num_syms; s++) {
+            unsigned l = lens[s];
+            if (l) a[s] = __brev(next[l]++) >> (32 - l);
+        }
+    }
+}
+
+}  // namespace bdf

@@ -17,7 +17,7 @@ def inputs():
     return corpus.small_cases() + [
         corpus.corpus_a_stream(0), corpus.corpus_a_stream(11), corpus.text_stream(1),
         corpus.binary_stream(2), corpus.lowentropy_stream(3), corpus.offset_stream(3),
-        corpus.offset_stream(32), corpus.text_stream(6, 70000),
+        corpus.offset_stream(32), corpus.text_stream(6, 65535), corpus.binary_stream(9, 65536),
         np.random.default_rng(5).integers(0, 256, 4000, dtype=np.uint8).tobytes(),
     ]
 
@@ -64,6 +64,14 @@ def test_compress_byte_identical_to_oracle(engine):
                 assert g == (exp if exp is not None else b""), (fmt, level, len(s))
                 if exp is not None and not (level == 0 and len(s) == 0):
                     assert zlib.decompress(g, WBITS[fmt]) == s
+
+
+def test_oversize_streams_fail_loudly(engine):
+    # levels >= 1 are limited to 64 KiB streams in this build: an error, never a silent empty result
+    big = corpus.text_stream(6, 70000)
+    with pytest.raises(engine.BdfError):
+        engine.BatchCompressor(6).compress_batch([big])
+    assert zlib.decompress(engine.BatchCompressor(0).compress_batch([big])[0], -15) == big
 
 
 def test_compress_failure_is_in_band(engine):
