@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <new>
@@ -37,6 +38,7 @@ struct bdf_ctx {
     unsigned long long *d_counters = nullptr;   // work-queue heads, one slot per launch in flight
     unsigned counter_slot = 0;
     int inflate_blocks_per_sm[3] = {0, 0, 0};
+    int inflate_group = 16;                     // lanes per stream in inflate_kernel (BDF_INFLATE_GROUP)
     bdf::DeflateScratch deflate_scratch;
     DevBuf in, out, in_off, out_off, max_out, out_size, status, checksum;
 };
@@ -83,25 +85,35 @@ unsigned long long *next_counter(bdf_ctx *ctx, cudaStream_t s)
     return c;
 }
 
-template <int FORMAT>
-int launch_inflate(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
+template <int FORMAT, int G>
+int launch_inflate_g(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
 {
-    const size_t smem = sizeof(bdf::InflateWarpSmem) * bdf::INF_WARPS_PER_BLOCK;
+    constexpr int groups = bdf::INF_THREADS / G;
+    const size_t smem = sizeof(bdf::InflateSmem) * groups;
     int &bps = ctx->inflate_blocks_per_sm[FORMAT];
     if (bps == 0) {
-        CK(cudaFuncSetAttribute(bdf::inflate_kernel<FORMAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(bdf::inflate_kernel<FORMAT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, bdf::inflate_kernel<FORMAT>,
-                                                         bdf::INF_WARPS_PER_BLOCK * 32, smem));
+        CK(cudaFuncSetAttribute(bdf::inflate_kernel<FORMAT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(bdf::inflate_kernel<FORMAT, G>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, bdf::inflate_kernel<FORMAT, G>, bdf::INF_THREADS, smem));
         if (bps < 1) bps = 1;
     }
-    unsigned long long want = ((unsigned long long)a.n + bdf::INF_WARPS_PER_BLOCK - 1) / bdf::INF_WARPS_PER_BLOCK;
+    unsigned long long want = ((unsigned long long)a.n + groups - 1) / groups;
     unsigned long long full = (unsigned long long)ctx->sm_count * bps;
     unsigned grid = (unsigned)(want < full ? want : full);
-    bdf::inflate_kernel<FORMAT><<<grid, bdf::INF_WARPS_PER_BLOCK * 32, smem, s>>>(a);
+    bdf::inflate_kernel<FORMAT, G><<<grid, bdf::INF_THREADS, smem, s>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
+}
+
+template <int FORMAT>
+int launch_inflate(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
+{
+    switch (ctx->inflate_group) {
+        case 32: return launch_inflate_g<FORMAT, 32>(ctx, a, s);
+        case 8: return launch_inflate_g<FORMAT, 8>(ctx, a, s);
+        default: return launch_inflate_g<FORMAT, 16>(ctx, a, s);
+    }
 }
 
 bool bad_format(int f) { return f != BDF_RAW && f != BDF_ZLIB && f != BDF_GZIP; }
@@ -128,6 +140,10 @@ int bdf_ctx_create(int device, bdf_ctx **out)
     bdf_ctx *ctx = new (std::nothrow) bdf_ctx();
     if (!ctx) return BDF_E_NOMEM;
     ctx->device = device;
+    if (const char *e = getenv("BDF_INFLATE_GROUP")) {
+        int v = atoi(e);
+        if (v == 8 || v == 16 || v == 32) ctx->inflate_group = v;
+    }
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);

@@ -5,7 +5,7 @@
 //   Adler-32: with 0-based byte index i, s1 = 1 + Σb and s2 = n + n·Σb − Σ i·b
 //   (mod 65521), so lanes sum (Σb, Σ i·b) over interleaved 16-byte vectors with
 //   dp4a and one warp reduction finishes the stream — the "vectorised reduction".
-//   CRC-32: see warp_crc32 (inflate.cuh) — per-lane slice-by-4 over contiguous
+//   CRC-32: see grp_crc32 (inflate.cuh) — per-lane slice-by-4 over contiguous
 //   slices, recombined with x^(8k) mod P multipliers.
 #pragma once
 #include "inflate.cuh"

@@ -60,6 +60,31 @@ __device__ __forceinline__ uint32_t gf2_xpow8n(uint64_t nbytes, const uint32_t *
     return p;
 }
 
+// ---- lane groups.  A warp is cut into 32/G groups of G consecutive lanes; each
+// group owns one stream and runs in lock-step on its own (sub-)mask, so one
+// warp instruction advances 32/G streams.  G = 32 is the classic warp-per-stream.
+template <int G>
+struct Grp {
+    static_assert(G == 4 || G == 8 || G == 16 || G == 32, "group size");
+    unsigned lane;    // lane index inside the group
+    unsigned shift;   // first warp lane of the group
+    unsigned mask;    // member mask of the group
+    __device__ __forceinline__ Grp()
+    {
+        const unsigned wl = threadIdx.x & 31u;
+        lane = wl & (unsigned)(G - 1);
+        shift = wl & ~(unsigned)(G - 1);
+        mask = G == 32 ? 0xFFFFFFFFu : (((1u << (G & 31)) - 1u) << shift);
+    }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    template <class T> __device__ __forceinline__ T shfl(T v, unsigned src) const { return __shfl_sync(mask, v, src, G); }
+    template <class T> __device__ __forceinline__ T shfl_xor(T v, unsigned d) const { return __shfl_xor_sync(mask, v, d, G); }
+    template <class T> __device__ __forceinline__ T shfl_up(T v, unsigned d) const { return __shfl_up_sync(mask, v, d, G); }
+    __device__ __forceinline__ unsigned ballot(bool p) const { return __ballot_sync(mask, p) >> shift; }
+    __device__ __forceinline__ unsigned match_any(unsigned v) const { return __match_any_sync(mask, v) >> shift; }
+    __device__ __forceinline__ unsigned lt_mask() const { return (1u << lane) - 1u; }
+};
+
 struct CrcTables {
     uint32_t slice[4][256];  // slice-by-4
     uint32_t x2n[32];

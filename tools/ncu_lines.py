@@ -58,9 +58,9 @@ def kernel_match(mangled, kernel):
     k = re.sub(r"[^A-Za-z0-9_]", "", kernel.split("<")[0].split("::")[-1])
     if k not in mangled:
         return False
-    m = re.search(r"<\(int\)(\d+)>", kernel)
-    if m:
-        return f"ILi{m.group(1)}E" in mangled
+    ints = re.findall(r"\(int\)(\d+)", kernel)
+    if ints:
+        return "I" + "".join(f"Li{v}E" for v in ints) + "E" in mangled
     return True
 
 
