@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(L0_WARPS_PER_BLOCK * 32) deflate_stored_kernel
     }
 }
 
-constexpr size_t HC_SCRATCH_PER_CTA = 32768 * sizeof(HcSeq);   // >= 65536/3 + 2 sequences
+constexpr size_t HC_SCRATCH_PER_CTA = HC_CHAIN_BYTES + (65536 + 64) * sizeof(uint32_t);   // chains + symbol records
 
 // Host-side dispatcher.  *why != nullptr with cudaSuccess means "unsupported".
 inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm_count, cudaStream_t s,
@@ -80,24 +80,40 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
     }
     if (a.level == 1) {
         const size_t smem = sizeof(L1Smem);
-        if (!scratch.l1_ready) {
-            *why = "cudaFuncSetAttribute(deflate_l1_kernel)";
-            e = cudaFuncSetAttribute(deflate_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static int l1_ctas_per_sm = 0;
+        if (l1_ctas_per_sm == 0) {
+            const char *env = getenv("BDF_L1_CTAS_PER_SM");
+            l1_ctas_per_sm = env && atoi(env) > 0 ? atoi(env) : 8;
+        }
+        const unsigned long long full = (unsigned long long)sm_count * l1_ctas_per_sm;
+        const unsigned long long want = ((unsigned long long)a.n + L1_WARPS - 1) / L1_WARPS;
+        const unsigned grid = (unsigned)(want < full ? want : full);
+        const size_t need = L1_TABLE_BYTES * L1_WARPS * (size_t)full;
+        if (scratch.cap < need) {
+            if (scratch.p) cudaFree(scratch.p);
+            scratch.p = nullptr;
+            scratch.cap = 0;
+            *why = "cudaMalloc(deflate scratch)";
+            e = cudaMalloc(&scratch.p, need);
             if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(deflate_l1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            if (e != cudaSuccess) return e;
-            scratch.l1_ready = true;
+            scratch.cap = need;
             *why = nullptr;
         }
-        unsigned long long full = (unsigned long long)sm_count * 3;
-        unsigned grid = (unsigned)(a.n < full ? a.n : full);
-        deflate_l1_kernel<<<grid, 32, smem, s>>>(a);
+        a.scratch = scratch.p;
+        a.scratch_stride = L1_TABLE_BYTES;
+        deflate_l1_kernel<<<grid, L1_WARPS * 32, smem, s>>>(a);
         *nlaunch = 1;
         return cudaGetLastError();
     }
     if (a.level <= 9) {
         const size_t smem = sizeof(HcSmem);
-        unsigned grid = (unsigned)(a.n < (unsigned)sm_count ? a.n : (unsigned)sm_count);
+        static int hc_ctas_per_sm = 0;
+        if (hc_ctas_per_sm == 0) {
+            const char *env = getenv("BDF_HC_CTAS_PER_SM");
+            hc_ctas_per_sm = env && atoi(env) > 0 ? atoi(env) : 8;
+        }
+        const unsigned full_grid = (unsigned)sm_count * (unsigned)hc_ctas_per_sm;
+        unsigned grid = a.n < full_grid ? a.n : full_grid;
         if (!scratch.hc_ready) {
             *why = "cudaFuncSetAttribute(deflate_hc_kernel)";
             e = cudaFuncSetAttribute(deflate_hc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -105,7 +121,7 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
             scratch.hc_ready = true;
             *why = nullptr;
         }
-        const size_t need = HC_SCRATCH_PER_CTA * (size_t)sm_count;
+        const size_t need = HC_SCRATCH_PER_CTA * (size_t)full_grid;
         if (scratch.cap < need) {
             if (scratch.p) cudaFree(scratch.p);
             scratch.p = nullptr;

@@ -26,21 +26,17 @@
 
 namespace bdf {
 
-constexpr int HC_THREADS = 256;
+constexpr int HC_THREADS = 128;
 constexpr int HC_WARPS = HC_THREADS / 32;
 constexpr uint32_t HC_MAX_LEN = 65536;
 constexpr uint32_t HC_WINDOW = 256;           // positions searched per round (max)
 constexpr uint32_t HC_NOPOS = 0xFFFFu;
 
-struct HcSeq {
-    uint32_t litrun;
-    uint16_t len;       // 0 terminates the block
-    uint16_t off;
-};
+// Symbol records written by the parse and consumed by the emitter, in stream order:
+// a literal is its byte value; a match is a length record followed by an offset record.
+constexpr uint32_t SYM_LEN = 0x10000u, SYM_OFF = 0x20000u;
 
 struct __align__(16) HcSmem {
-    uint16_t head[32768];              // bucket -> most recent position, 0xFFFF = empty
-    uint16_t link[65536];              // position -> distance to previous same-hash position, 0 = none
     uint16_t mlen[HC_WINDOW], moff[HC_WINDOW];
     uint32_t litlen_freq[288], offset_freq[32];
     uint32_t litlen_code[288], offset_code[32];     // bit-reversed codewords
@@ -58,6 +54,18 @@ struct __align__(16) HcSmem {
     uint32_t pre_freq[19], pre_code[19];
     uint8_t pre_len[19];
 };
+
+// Hash chains of one stream.  They live in global memory (a per-CTA slab that stays
+// L2-resident while the stream is being parsed) rather than in shared memory, so that
+// many streams are in flight per SM and the serial parse of one hides behind the
+// chain walks of the others.
+//   head[32768]: bucket -> most recent position, 0xFFFF = empty
+//   link[65536]: position -> distance to the previous same-hash position, 0 = none
+struct HcChains {
+    uint16_t *head;
+    uint16_t *link;
+};
+constexpr size_t HC_CHAIN_BYTES = (32768 + 65536) * sizeof(uint16_t);
 
 struct HcParams { unsigned max_depth, nice_len, lazy; };
 __device__ __forceinline__ HcParams hc_params(int level)
@@ -79,7 +87,7 @@ __device__ __forceinline__ HcParams hc_params(int level)
 
 // Insert positions [from, to) (warp 0, all lanes).  Positions with fewer than
 // 3 bytes left are never inserted (matchfinder.rs:765,1021).
-__device__ __forceinline__ void hc_insert_range(HcSmem &sm, const uint8_t *in, uint32_t len, uint32_t from,
+__device__ __forceinline__ void hc_insert_range(const HcChains &ch, const uint8_t *in, uint32_t len, uint32_t from,
                                                 uint32_t to, unsigned lane)
 {
     for (uint32_t base = from; base < to; base += 32) {
@@ -90,29 +98,44 @@ __device__ __forceinline__ void hc_insert_range(HcSmem &sm, const uint8_t *in, u
         const unsigned peers = __match_any_sync(BDF_FULL_MASK, h);
         const unsigned lower = peers & lanemask_lt();
         if (ok) {
-            uint32_t prev = lower ? base + (31 - __clz(lower)) : sm.head[h];
-            sm.link[p] = prev == HC_NOPOS ? 0 : (uint16_t)(p - prev);   // distance <= 65535 always fits
+            uint32_t prev = lower ? base + (31 - __clz(lower)) : ch.head[h];
+            ch.link[p] = prev == HC_NOPOS ? 0 : (uint16_t)(p - prev);   // distance <= 65535 always fits
         }
         __syncwarp();
-        if (ok && (peers >> lane) == 1u) sm.head[h] = (uint16_t)p;
+        if (ok && (peers >> lane) == 1u) ch.head[h] = (uint16_t)p;
         __syncwarp();
     }
 }
 
+// 4 bytes at any alignment from the aligned words that contain them (never touches a word
+// without a requested byte, so it stays inside the stream)
+__device__ __forceinline__ uint32_t ld32_any(const uint8_t *p)
+{
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(p - sh);
+    const uint32_t lo = w[0];
+    if (sh == 0) return lo;
+    return __funnelshift_r(lo, w[1], 8 * sh);
+}
 __device__ __forceinline__ unsigned prefix_len_bytes(const uint8_t *a, const uint8_t *b, unsigned maxlen)
 {
     unsigned n = 0;
+    while (n + 4 <= maxlen) {
+        const uint32_t x = ld32_any(a + n) ^ ld32_any(b + n);
+        if (x) return n + ((__ffs(x) - 1) >> 3);
+        n += 4;
+    }
     while (n < maxlen && a[n] == b[n]) n++;
     return n;
 }
 
 // find_match_impl without the insertion (already done): walk the chain of p.
-__device__ __forceinline__ void hc_search(const HcSmem &sm, const uint8_t *in, uint32_t len, uint32_t p,
+__device__ __forceinline__ void hc_search(const HcChains &ch, const uint8_t *in, uint32_t len, uint32_t p,
                                           const HcParams &prm, unsigned &out_len, unsigned &out_off)
 {
     out_len = 0; out_off = 0;
     if (p + 3 > len) return;
-    const uint32_t first = sm.link[p];
+    const uint32_t first = ch.link[p];
     if (!first) return;
     const bool can4 = p + 4 <= len;
     const uint8_t *src = in + p;
@@ -148,7 +171,7 @@ __device__ __forceinline__ void hc_search(const HcSmem &sm, const uint8_t *in, u
         }
         // prev_tab is indexed modulo 32768 in the reference: a candidate exactly one
         // window back reads the slot the current position has just overwritten
-        const uint32_t lk = off == 32768u ? first : sm.link[cur];
+        const uint32_t lk = off == 32768u ? first : ch.link[cur];
         if (!lk) break;
         cur -= (int32_t)lk;
         depth++;
@@ -235,14 +258,18 @@ __device__ void hc_prepare_header(HcSmem &sm, unsigned &nlit, unsigned &noff, un
     while (npre > 4 && sm.pre_len[perm[npre - 1]] == 0) npre--;
 }
 
-__global__ void __launch_bounds__(HC_THREADS, 1) deflate_hc_kernel(DeflateArgs a)
+__global__ void __launch_bounds__(HC_THREADS) deflate_hc_kernel(DeflateArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HcSmem &sm = *reinterpret_cast<HcSmem *>(smem_raw);
     __shared__ unsigned long long s_idx;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const HcParams prm = hc_params(a.level);
-    HcSeq *seqs = reinterpret_cast<HcSeq *>(static_cast<uint8_t *>(a.scratch) + a.scratch_stride * blockIdx.x);
+    uint8_t *slab = static_cast<uint8_t *>(a.scratch) + a.scratch_stride * blockIdx.x;
+    HcChains ch;
+    ch.head = reinterpret_cast<uint16_t *>(slab);
+    ch.link = ch.head + 32768;
+    uint32_t *syms = reinterpret_cast<uint32_t *>(slab + HC_CHAIN_BYTES);
     if (a.format == BDF_GZIP) load_crc_tables_to_smem(sm.crc, sm.x2n);
 
     for (;;) {
@@ -259,7 +286,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) deflate_hc_kernel(DeflateArgs a
             continue;
         }
         const uint32_t len = (uint32_t)len64;
-        for (unsigned i = tid; i < 32768 / 2; i += HC_THREADS) reinterpret_cast<uint32_t *>(sm.head)[i] = 0xFFFFFFFFu;
+        for (unsigned i = tid; i < 32768 / 8; i += HC_THREADS) reinterpret_cast<uint4 *>(ch.head)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
         unsigned hdr = 0;
         BitSink bs;
         if (warp == 0) {
@@ -277,7 +304,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) deflate_hc_kernel(DeflateArgs a
         do {
             // ------------------------------------------------ one block
             const uint32_t block_start = p;
-            uint32_t nseq = 0, litrun = 0;
+            uint32_t nsym = 0;          // warp 0: symbol records of this block
             for (unsigned i = tid; i < 288; i += HC_THREADS) sm.litlen_freq[i] = 0;
             if (tid < 32) sm.offset_freq[tid] = 0;
             if (tid < 14) { sm.new_obs[tid] = 0; sm.obs[tid] = 0; }
@@ -288,19 +315,21 @@ __global__ void __launch_bounds__(HC_THREADS, 1) deflate_hc_kernel(DeflateArgs a
                 // 1. make sure [p, p + window) is inserted, then search it
                 if (warp == 0) {
                     uint32_t to = p + window < len ? p + window : len;
-                    if (to > ins_end) { hc_insert_range(sm, in, len, ins_end, to, lane); ins_end = to; }
+                    if (to > ins_end) { hc_insert_range(ch, in, len, ins_end, to, lane); ins_end = to; }
                     if (lane == 0) { sm.c_search_from = p; sm.c_search_to = to; }
                 }
                 __syncthreads();
                 const uint32_t sfrom = sm.c_search_from, sto = sm.c_search_to;
                 for (uint32_t q = sfrom + tid; q < sto; q += HC_THREADS) {
                     unsigned l, o;
-                    hc_search(sm, in, len, q, prm, l, o);
+                    hc_search(ch, in, len, q, prm, l, o);
                     sm.mlen[q - sfrom] = (uint16_t)l;
                     sm.moff[q - sfrom] = (uint16_t)o;
                 }
                 __syncthreads();
-                // 2. serial parse by warp 0 (decide_greedy_sequences)
+                // 2. parse by warp 0 (decide_greedy_sequences).  Literal runs are handled 32 positions
+                //    at a time; the split check, which only acts once 2048 observations are pending,
+                //    is evaluated exactly where the serial loop would act on it (see n_safe below).
                 if (warp == 0) {
                     bool jumped = false;
                     while (p < len) {
@@ -309,49 +338,71 @@ __global__ void __launch_bounds__(HC_THREADS, 1) deflate_hc_kernel(DeflateArgs a
                         bool end_block = false;
                         if (lane == 0) end_block = hc_should_end(sm, p - block_start, len - p);
                         end_block = __shfl_sync(BDF_FULL_MASK, end_block, 0);
+                        __syncwarp();
                         if (end_block) { block_done = true; break; }
                         unsigned l = sm.mlen[p - sfrom], o = sm.moff[p - sfrom];
-                        if (l >= 3) {
-                            unsigned nlit = 0;      // literals emitted by a lazy decision
-                            if (prm.lazy >= 1 && p + 1 < len && l < prm.nice_len) {
-                                const unsigned l1 = sm.mlen[p + 1 - sfrom];
-                                if (l1 > l) {
-                                    nlit = 1; l = l1; o = sm.moff[p + 1 - sfrom];
-                                    if (prm.lazy >= 2 && p + 2 < len) {
-                                        const unsigned l2 = sm.mlen[p + 2 - sfrom];
-                                        if (l2 > l1) { nlit = 2; l = l2; o = sm.moff[p + 2 - sfrom]; }
-                                    }
+                        if (l < 3) {
+                            // literals up to the next match start, the window end, or the next position
+                            // at which should_end_block could change state
+                            const uint32_t pending = sm.num_new;
+                            uint32_t n_safe;
+                            if (pending < 2048) n_safe = 2048 - pending;
+                            else if (len - p <= 5000) n_safe = 0xFFFFFFFFu;
+                            else n_safe = 5000 - (p - block_start);     // block_len < 5000 here
+                            uint32_t limit = sto - p < n_safe ? sto : p + n_safe;
+                            uint32_t n = 0;
+                            for (;;) {
+                                const uint32_t q = p + n + lane;
+                                const bool lit = q < limit && sm.mlen[q - sfrom] < 3;
+                                const unsigned stop = __ballot_sync(BDF_FULL_MASK, !lit);
+                                const unsigned take = stop ? __ffs(stop) - 1 : 32;
+                                if (lane < take) {
+                                    const unsigned b = in[q];
+                                    atomicAdd(&sm.litlen_freq[b], 1u);
+                                    atomicAdd(&sm.new_obs[b >> 5], 1u);
+                                    syms[nsym + n + lane] = b;
+                                }
+                                n += take;
+                                if (take < 32) break;
+                            }
+                            __syncwarp();
+                            if (lane == 0) sm.num_new = pending + n;
+                            __syncwarp();
+                            nsym += n;
+                            p += n;
+                            continue;
+                        }
+                        unsigned nlit = 0;      // literals emitted by a lazy decision
+                        if (prm.lazy >= 1 && p + 1 < len && l < prm.nice_len) {
+                            const unsigned l1 = sm.mlen[p + 1 - sfrom];
+                            if (l1 > l) {
+                                nlit = 1; l = l1; o = sm.moff[p + 1 - sfrom];
+                                if (prm.lazy >= 2 && p + 2 < len) {
+                                    const unsigned l2 = sm.mlen[p + 2 - sfrom];
+                                    if (l2 > l1) { nlit = 2; l = l2; o = sm.moff[p + 2 - sfrom]; }
                                 }
                             }
-                            if (lane == 0) {
-                                for (unsigned k = 0; k < nlit; k++) {
-                                    const unsigned b = in[p + k];
-                                    sm.new_obs[b >> 5]++; sm.num_new++;
-                                    sm.litlen_freq[b]++;
-                                }
-                                const unsigned slot = offset_slot_of(o);
-                                seqs[nseq].litrun = litrun + nlit;
-                                seqs[nseq].len = (uint16_t)l;
-                                seqs[nseq].off = (uint16_t)o;
-                                sm.new_obs[8 + (l >= 8)]++;
-                                sm.new_obs[10 + (slot < 16 ? 0 : slot < 24 ? 1 : slot < 30 ? 2 : 0)]++;
-                                sm.num_new += 2;
-                                sm.litlen_freq[257 + length_slot_of(l)]++;
-                                sm.offset_freq[slot]++;
-                            }
-                            nseq++;
-                            litrun = 0;
-                            p += nlit + l;
-                            if (p >= sto) jumped = l >= 32;
-                        } else {
-                            if (lane == 0) {
-                                const unsigned b = in[p];
+                        }
+                        if (lane == 0) {
+                            for (unsigned k = 0; k < nlit; k++) {
+                                const unsigned b = in[p + k];
                                 sm.new_obs[b >> 5]++; sm.num_new++;
                                 sm.litlen_freq[b]++;
+                                syms[nsym + k] = b;
                             }
-                            litrun++;
-                            p++;
+                            const unsigned slot = offset_slot_of(o);
+                            syms[nsym + nlit] = SYM_LEN | l;
+                            syms[nsym + nlit + 1] = SYM_OFF | o;
+                            sm.new_obs[8 + (l >= 8)]++;
+                            sm.new_obs[10 + (slot < 16 ? 0 : slot < 24 ? 1 : slot < 30 ? 2 : 0)]++;
+                            sm.num_new += 2;
+                            sm.litlen_freq[257 + length_slot_of(l)]++;
+                            sm.offset_freq[slot]++;
                         }
+                        __syncwarp();
+                        nsym += nlit + 2;
+                        p += nlit + l;
+                        if (p >= sto) jumped = l >= 32;
                     }
                     if (p >= len) block_done = true;
                     window = jumped ? 32 : HC_WINDOW;
@@ -363,11 +414,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) deflate_hc_kernel(DeflateArgs a
             }
             // ------------------------------------------------ block end: codes + emission (warp 0)
             if (warp == 0) {
-                if (lane == 0) {
-                    seqs[nseq].litrun = litrun; seqs[nseq].len = 0; seqs[nseq].off = 0;
-                    sm.litlen_freq[256]++;
-                }
-                nseq++;
+                if (lane == 0) sm.litlen_freq[256]++;
                 __syncwarp();
                 __threadfence_block();
                 unsigned nlit_syms = 0, noff_syms = 0, npre = 0, nitems = 0;
@@ -402,37 +449,28 @@ __global__ void __launch_bounds__(HC_THREADS, 1) deflate_hc_kernel(DeflateArgs a
                     }
                     bs.put(bits, nb, lane);
                 }
-                // symbols: literals 32 at a time, then the match as two items
-                uint32_t at = block_start;
-                for (uint32_t s = 0; s < nseq; s++) {
-                    const HcSeq sq = seqs[s];
-                    for (uint32_t base = 0; base < sq.litrun; base += 32) {
-                        uint32_t bits = 0, nb = 0;
-                        if (base + lane < sq.litrun) {
-                            const unsigned b = in[at + base + lane];
-                            bits = sm.litlen_code[b]; nb = sm.litlen_len[b];
-                        }
-                        bs.put(bits, nb, lane);
-                    }
-                    at += sq.litrun;
-                    if (sq.len >= 3) {
-                        uint32_t bits = 0, nb = 0;
-                        if (lane == 0) {
-                            unsigned slot = length_slot_of(sq.len), base, extra;
-                            length_slot_info(slot, base, extra);
+                // symbols, 32 records per step: literal / length / offset records in stream order
+                for (uint32_t base = 0; base < nsym; base += 32) {
+                    uint32_t bits = 0, nb = 0;
+                    if (base + lane < nsym) {
+                        const uint32_t rec = syms[base + lane], v = rec & 0xFFFFu;
+                        if (rec < SYM_LEN) {
+                            bits = sm.litlen_code[v]; nb = sm.litlen_len[v];
+                        } else if (rec < SYM_OFF) {
+                            unsigned slot = length_slot_of(v), lb, le;
+                            length_slot_info(slot, lb, le);
                             const unsigned cl = sm.litlen_len[257 + slot];
-                            bits = sm.litlen_code[257 + slot] | ((sq.len - base) << cl);
-                            nb = cl + extra;
-                        } else if (lane == 1) {
-                            unsigned slot = offset_slot_of(sq.off), base, extra;
-                            offset_slot_info(slot, base, extra);
+                            bits = sm.litlen_code[257 + slot] | ((v - lb) << cl);
+                            nb = cl + le;
+                        } else {
+                            unsigned slot = offset_slot_of(v), ob, oe;
+                            offset_slot_info(slot, ob, oe);
                             const unsigned cl = sm.offset_len[slot];
-                            bits = sm.offset_code[slot] | ((sq.off - base) << cl);
-                            nb = cl + extra;
+                            bits = sm.offset_code[slot] | ((v - ob) << cl);
+                            nb = cl + oe;
                         }
-                        bs.put(bits, nb, lane);
-                        at += sq.len;
                     }
+                    bs.put(bits, nb, lane);
                 }
                 bs.put1(sm.litlen_code[256], sm.litlen_len[256], lane);
             }

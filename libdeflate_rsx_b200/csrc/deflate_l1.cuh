@@ -20,9 +20,15 @@ namespace bdf {
 constexpr uint32_t L1_MAX_LEN = 65536;
 constexpr uint32_t L1_EMPTY = 0xFFFFu;
 
+constexpr int L1_WARPS = 4;                      // streams per CTA
+constexpr size_t L1_TABLE_BYTES = 32768 * sizeof(uint16_t);
+
+// The 64 KiB hash table of each stream (last position per bucket, 0xFFFF = empty) lives in
+// a per-warp global slab that stays L2-resident while the stream is parsed: in shared
+// memory it would cap the SM at three streams, and this parse is a chain of dependent
+// probes that only many streams in flight can hide.
 struct __align__(16) L1Smem {
-    uint16_t table[32768];          // 64 KiB: last position per hash bucket, 0xFFFF = empty
-    uint32_t sink[SINK_WORDS];
+    uint32_t sink[L1_WARPS][SINK_WORDS];
     uint32_t crc[4][256];
     uint32_t x2n[32];
 };
@@ -51,11 +57,13 @@ __device__ __forceinline__ void static_off_code(unsigned off, uint32_t &bits, ui
     n = 5 + extra;
 }
 
-__global__ void __launch_bounds__(32) deflate_l1_kernel(DeflateArgs a)
+__global__ void __launch_bounds__(L1_WARPS * 32) deflate_l1_kernel(DeflateArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     L1Smem &sm = *reinterpret_cast<L1Smem *>(smem_raw);
-    const unsigned lane = lane_id();
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    uint16_t *table = reinterpret_cast<uint16_t *>(static_cast<uint8_t *>(a.scratch) +
+                                                   a.scratch_stride * (blockIdx.x * L1_WARPS + warp));
     if (a.format == BDF_GZIP) load_crc_tables_to_smem(sm.crc, sm.x2n);
     for (;;) {
         unsigned long long idx = 0;
@@ -70,10 +78,10 @@ __global__ void __launch_bounds__(32) deflate_l1_kernel(DeflateArgs a)
             continue;
         }
         const uint32_t len = (uint32_t)len64;
-        for (unsigned i = lane; i < 32768 / 2; i += 32) reinterpret_cast<uint32_t *>(sm.table)[i] = 0xFFFFFFFFu;
+        for (unsigned i = lane; i < 32768 / 8; i += 32) reinterpret_cast<uint4 *>(table)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
         const unsigned hdr = frame_header(a.format, 1, out, lane);
         BitSink bs;
-        bs.init(sm.sink, out + hdr, deflate_bound(len), lane);
+        bs.init(sm.sink[warp], out + hdr, deflate_bound(len), lane);
         bs.put1(3, 3, lane);                     // BFINAL = 1, BTYPE = 01
 
         uint32_t pos = 0;
@@ -85,14 +93,14 @@ __global__ void __launch_bounds__(32) deflate_l1_kernel(DeflateArgs a)
             const unsigned peers = __match_any_sync(BDF_FULL_MASK, h);
             const unsigned lower = peers & lanemask_lt();
             uint32_t cand = L1_EMPTY;
-            if (hashable) cand = lower ? pos + (31 - __clz(lower)) : sm.table[h];
+            if (hashable) cand = lower ? pos + (31 - __clz(lower)) : table[h];
             const bool found = hashable && cand != L1_EMPTY && p - cand <= 32768u && ld24(in + cand) == v;
             const unsigned fb = __ballot_sync(BDF_FULL_MASK, found);
             const unsigned k = fb ? __ffs(fb) - 1 : 32;            // first lane whose probe hits
             // commit bucket writes of lanes 0..k (the match start is inserted too, :1162-1163)
             const unsigned committing = __ballot_sync(BDF_FULL_MASK, hashable && lane <= k);
             const unsigned mine = peers & committing;
-            if (hashable && lane <= k && (mine >> lane) == 1u) sm.table[h] = (uint16_t)p;
+            if (hashable && lane <= k && (mine >> lane) == 1u) table[h] = (uint16_t)p;
             // literals: lanes below k that are inside the input
             uint32_t bits = 0, nb = 0;
             if (lane < k && p < len) static_lit_code(in[p], bits, nb);
