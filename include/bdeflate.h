@@ -117,7 +117,7 @@ int bdf_decompress_batch_host(bdf_ctx *ctx, int format, const uint8_t *in,
  * out + out_off[i]; a stream whose encoding does not fit fails with
  * BDF_INSUFFICIENT_SPACE and out_size[i] = 0 — the reference has no
  * stored-block fallback (src/compress/mod.rs:641-644).
- * Limits of this build: levels 10..12 return BDF_E_UNSUPPORTED; at levels >= 1
+ * Limit of this build: at levels >= 1
  * a stream longer than 65536 bytes is not compressed — the *_host call returns
  * BDF_E_UNSUPPORTED before doing any work, the *_device call (which cannot see
  * the lengths) sets status[i] = BDF_STREAM_UNSUPPORTED for that stream.

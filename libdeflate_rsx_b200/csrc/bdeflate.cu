@@ -314,7 +314,6 @@ int bdf_compress_batch_host(bdf_ctx *ctx, int level, int format, const uint8_t *
     if (n == 0) return BDF_E_OK;
     if (!in || !in_off || !out || !out_off || !out_size || !status) return fail(ctx, BDF_E_ARG, "null pointer");
     size_t in_bytes, out_bytes = 0;
-    if (level >= 10) return fail(ctx, BDF_E_UNSUPPORTED, "compression levels 10-12 are not implemented yet");
     if (level >= 1)
         for (size_t i = 0; i < n; i++)
             if (in_off[i + 1] - in_off[i] > 65536)

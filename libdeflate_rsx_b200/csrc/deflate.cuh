@@ -6,9 +6,10 @@
 //   level 0      deflate_stored_kernel   (this file)
 //   level 1      deflate_l1_kernel       (deflate_l1.cuh)
 //   levels 2..9  deflate_hc_kernel       (deflate_hc.cuh)
-//   levels 10..12: not built yet (ratio-tolerance tier) -> BDF_E_UNSUPPORTED
+//   levels 10..12 deflate_bt_kernel    (deflate_bt.cuh)
 #pragma once
 #include "deflate_common.cuh"
+#include "deflate_bt.cuh"
 #include "deflate_hc.cuh"
 #include "deflate_l1.cuh"
 
@@ -138,8 +139,32 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
         *nlaunch = 1;
         return cudaGetLastError();
     }
-    *why = "compression level not implemented yet (levels 10-12)";
-    return cudaSuccess;
+    {
+        static int bt_threads_per_sm = 0;
+        if (bt_threads_per_sm == 0) {
+            const char *env = getenv("BDF_BT_THREADS_PER_SM");
+            bt_threads_per_sm = env && atoi(env) > 0 ? atoi(env) : 128;
+        }
+        const unsigned long long full = (unsigned long long)sm_count * bt_threads_per_sm / BT_THREADS;
+        const unsigned long long want = ((unsigned long long)a.n + BT_THREADS - 1) / BT_THREADS;
+        const unsigned grid = (unsigned)(want < full ? want : full);
+        const size_t need = BT_SLAB_BYTES * (size_t)grid * BT_THREADS;
+        if (scratch.cap < need) {
+            if (scratch.p) cudaFree(scratch.p);
+            scratch.p = nullptr;
+            scratch.cap = 0;
+            *why = "cudaMalloc(deflate scratch)";
+            e = cudaMalloc(&scratch.p, need);
+            if (e != cudaSuccess) return e;
+            scratch.cap = need;
+            *why = nullptr;
+        }
+        a.scratch = scratch.p;
+        a.scratch_stride = BT_SLAB_BYTES;
+        deflate_bt_kernel<<<grid, BT_THREADS, 0, s>>>(a);
+        *nlaunch = 1;
+        return cudaGetLastError();
+    }
 }
 
 }  // namespace bdf

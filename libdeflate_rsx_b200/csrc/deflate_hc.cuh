@@ -180,7 +180,8 @@ __device__ __forceinline__ void hc_search(const HcChains &ch, const uint8_t *in,
 }
 
 // BlockSplitStats::should_end_block, src/compress/mod.rs:387-415 (+ :359-384); thread-0 only
-__device__ bool hc_should_end(HcSmem &sm, uint32_t block_len, uint32_t remaining)
+template <class S>
+__device__ bool hc_should_end(S &sm, uint32_t block_len, uint32_t remaining)
 {
     if (sm.num_new < 2048 && block_len < 300000u) return false;
     if (remaining <= 5000u) return false;
@@ -208,7 +209,8 @@ __device__ bool hc_should_end(HcSmem &sm, uint32_t block_len, uint32_t remaining
 
 // write_dynamic_huffman_header_impl, src/compress/mod.rs:1775-1883.  Thread 0 computes
 // the run-length items and the precode; the caller's warp then packs the bits.
-__device__ void hc_prepare_header(HcSmem &sm, unsigned &nlit, unsigned &noff, unsigned &npre, unsigned &nitems)
+template <class S>
+__device__ void hc_prepare_header(S &sm, unsigned &nlit, unsigned &noff, unsigned &npre, unsigned &nitems)
 {
     nlit = 288; noff = 32;
     while (nlit > 257 && sm.litlen_len[nlit - 1] == 0) nlit--;

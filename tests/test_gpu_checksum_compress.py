@@ -52,12 +52,16 @@ def levels_implemented(engine):
 
 
 def test_compress_byte_identical_to_oracle(engine):
-    """Levels 0..9: byte-identical to the oracle (the repository's definition of
-    the reference's output); every stream also inflates under system zlib."""
-    lv = [l for l in levels_implemented(engine) if l <= 9]
-    assert 0 in lv
+    """Levels 0..12: byte-identical to the oracle (the repository's definition of
+    the reference's output); every stream also inflates under system zlib.
+    (Levels 10..12 only owe a 0.5 % ratio; the GPU kernel follows the reference's
+    algorithm step for step, so they are held to identity too.)"""
+    lv = levels_implemented(engine)
+    assert lv == list(range(0, 13))
     for fmt in (0, 1, 2):
         for level in lv:
+            if level >= 10 and fmt != (level - 10):      # one framing per near-optimal level keeps the test short
+                continue
             got = engine.BatchCompressor(level, format=fmt).compress_batch(inputs())
             for g, s in zip(got, inputs()):
                 exp = o.compress(s, level, fmt)
@@ -87,8 +91,7 @@ def test_compress_ratio_tier(engine):
     """Levels 10..12: total compressed size within 0.5 % of the oracle's, and
     every stream round-trips through zlib."""
     lv = [l for l in levels_implemented(engine) if l >= 10]
-    if not lv:
-        pytest.skip("levels 10-12 not implemented in this round")
+    assert lv == [10, 11, 12]
     ins = [s for s in inputs() if len(s) >= 1000]
     for level in lv:
         got = engine.BatchCompressor(level).compress_batch(ins)
