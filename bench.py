@@ -273,6 +273,10 @@ def main():
     barrier()
     clocks.stop()
     launches = ctx.kernel_launches - launches0
+    if world > 1:
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())          # whole-job count, like `value`
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
