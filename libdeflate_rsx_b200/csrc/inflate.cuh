@@ -344,14 +344,35 @@ __device__ __forceinline__ uint32_t merge_word(uint32_t a, uint32_t b, int t)
     return __byte_perm(a, b, sel);
 }
 
+// x mod offset through a float reciprocal (x < 2^17): the quotient estimate is off by at most one
+__device__ __forceinline__ uint32_t mod_period(uint32_t x, uint32_t offset, float inv)
+{
+    uint32_t j = x - (uint32_t)((float)x * inv) * offset;
+    if ((int32_t)j < 0) j += offset;
+    if (j >= offset) j -= offset;
+    return j;
+}
+
+// rare path (period shorter than a chunk, or a match at the very start of the output), kept
+// out of line so that the hot decode loop stays small
+__device__ __noinline__ uint4 chunk_gather(const uint8_t *pat, uint32_t j, uint32_t offset)
+{
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        w[k >> 2] |= (uint32_t)pat[j] << (8 * (k & 3));
+        j = j + 1 == offset ? 0 : j + 1;
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // Source bytes of one 16-byte chunk at match-relative offset rel (see copy_match).
 // mode 0: offset >= length (plain run); 1: periodic, period >= 16 and the 16 bytes in front of the
 // period are addressable; 2: anything else (short period / start of output) -> byte gather.
 __device__ __forceinline__ uint4 chunk_source(const uint8_t *pat, uint32_t rel, uint32_t offset, float inv, int mode)
 {
     if (mode == 0) return load16_unaligned(pat + rel);
-    uint32_t j = rel - (uint32_t)((float)rel * inv) * offset;
-    if (j >= offset) j -= offset;
+    uint32_t j = mod_period(rel, offset, inv);
     if (mode == 1) {
         // a chunk is one contiguous run of the period (A), or its end followed by its start (A then B)
         const int t = (int)(offset - j);              // bytes left in this period, >= 1
@@ -361,13 +382,7 @@ __device__ __forceinline__ uint4 chunk_source(const uint8_t *pat, uint32_t rel, 
         return make_uint4(merge_word(a.x, b.x, t), merge_word(a.y, b.y, t - 4), merge_word(a.z, b.z, t - 8),
                           merge_word(a.w, b.w, t - 12));
     }
-    uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        w[k >> 2] |= (uint32_t)pat[j] << (8 * (k & 3));
-        j = j + 1 == offset ? 0 : j + 1;
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
+    return chunk_gather(pat, j, offset);
 }
 
 // One pass; every source byte lies in front of the match, so ALL loads (ragged
@@ -409,12 +424,7 @@ __device__ __forceinline__ void copy_match(const Grp<G> &g, OutState &o, unsigne
         eb[r] = 0;
         if (e < nedge) {
             const uint32_t ei = e < head ? e : nbody * 16 + e;    // tail bytes follow the body
-            uint32_t j = ei;
-            if (wrap) {
-                j = ei - (uint32_t)((float)ei * inv) * offset;
-                if (j >= offset) j -= offset;
-            }
-            eb[r] = pat[j];
+            eb[r] = pat[wrap ? mod_period(ei, offset, inv) : ei];
         }
     }
 #pragma unroll
@@ -440,10 +450,32 @@ __device__ __forceinline__ void copy_match(const Grp<G> &g, OutState &o, unsigne
             adler_acc16<ADLER>(o, dpos + rel, cv[r]);
         }
     }
+    // coalesced runs of matches can be much longer than 258 bytes: remaining chunks, one per lane
+    // per step (the source never overlaps what this call writes: it is the period in front of
+    // dpos, or for offset >= length the bytes in front of it)
+#pragma unroll 1
+    for (uint32_t c = g.lane + BR * G; c < nbody; c += G) {
+        const uint32_t rel = head + 16 * c;
+        const uint4 v = chunk_source(pat, rel, offset, inv, mode);
+        *reinterpret_cast<uint4 *>(base + dpos + rel) = v;
+        adler_acc16<ADLER>(o, dpos + rel, v);
+    }
     o.pos += length;
 }
 
 // ------------------------------------------------------------ block decoding
+// Consecutive matches with the same offset are one longer match with that offset (each one
+// continues the same period).  After a long match the decoder therefore looks ahead: while the
+// next symbol is another match with the same offset it is folded into the current one, so that
+// periodic / run-length data costs one long, fully populated copy instead of hundreds of
+// 258-byte ones.  The look-ahead works on a copy of the bit reader and is simply dropped when
+// the next symbol turns out to be something else; short matches (text) never pay for it.
+#ifndef BDF_COALESCE_MAX
+#define BDF_COALESCE_MAX (1u << 16)
+#endif
+constexpr uint32_t COALESCE_MAX = BDF_COALESCE_MAX;
+constexpr uint32_t COALESCE_MIN_LEN = 64;
+
 template <bool ADLER, int G>
 __device__ int decode_huffman_block(const Grp<G> &g, BitReader &br, OutState &o, InflateSmem &sm)
 {
@@ -470,7 +502,7 @@ __device__ int decode_huffman_block(const Grp<G> &g, BitReader &br, OutState &o,
         if (kind == K_EOB) {
             return br.overrun() ? BDF_SHORT_INPUT : BDF_OK;
         }
-        const unsigned length = (e >> 16) + br.take((e >> 5) & 15u);
+        unsigned length = (e >> 16) + br.take((e >> 5) & 15u);
         br.refill();
         uint32_t f = sm.off_tab[br.peek(OT_BITS)];
         if ((f & 31u) == 0) {
@@ -482,6 +514,28 @@ __device__ int decode_huffman_block(const Grp<G> &g, BitReader &br, OutState &o,
         flush_literals<ADLER>(o, g.lane);
         if (offset > o.pos) return BDF_BAD_DATA;
         if (o.pos + length > o.cap) return BDF_INSUFFICIENT_SPACE;
+        if (length >= COALESCE_MIN_LEN && COALESCE_MAX) {
+#pragma unroll 1
+            for (;;) {
+                BitReader t = br;
+                if (t.widx > t.nwords + 2) break;
+                t.refill();
+                uint32_t e2 = sm.lit_tab[t.peek(LT_BITS)];
+                if ((e2 & 31u) == 0) e2 = decode_long<CODE_LITLEN, LT_BITS>(t.peek(15), sm.lit_sorted, sm.lit_code);
+                if ((e2 & 31u) == 0 || (e2 & K_MASK) != K_BASE) break;
+                t.drop(e2 & 31u);
+                const unsigned len2 = (e2 >> 16) + t.take((e2 >> 5) & 15u);
+                t.refill();
+                uint32_t f2 = sm.off_tab[t.peek(OT_BITS)];
+                if ((f2 & 31u) == 0) f2 = decode_long<CODE_OFFSET, OT_BITS>(t.peek(15), sm.off_sorted, sm.off_code);
+                if ((f2 & 31u) == 0) break;
+                t.drop(f2 & 31u);
+                const unsigned off2 = (f2 >> 16) + t.take((f2 >> 5) & 15u);
+                if (off2 != offset || length + len2 > COALESCE_MAX || o.pos + length + len2 > o.cap) break;
+                br = t;
+                length += len2;
+            }
+        }
         make_valid<G>(g, o, o.pos + length + G);      // also covers the next literal flush
         copy_match<ADLER, G>(g, o, length, offset);
         if (ADLER) adler_fold(o);

@@ -27,6 +27,10 @@ def inputs():
         corpus.offset_stream(3), corpus.offset_stream(7), corpus.offset_stream(32),
         np.random.default_rng(5).integers(0, 256, 70000, dtype=np.uint8).tobytes(),
         (corpus.text_stream(5) * 6)[:300000],
+        # long same-offset match runs (coalesced copies): periods 40, 300 and 20000, > 64 KiB each
+        (corpus.text_stream(7, 40) * 8000)[:250001],
+        (corpus.binary_stream(8, 300) * 900)[:200003],
+        (corpus.text_stream(9, 20000) * 8)[:150000],
     ]
 
 
