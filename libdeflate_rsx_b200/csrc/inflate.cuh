@@ -368,11 +368,15 @@ __device__ __noinline__ uint4 chunk_gather(const uint8_t *pat, uint32_t j, uint3
 
 // Source bytes of one 16-byte chunk at match-relative offset rel (see copy_match).
 // mode 0: offset >= length (plain run); 1: periodic, period >= 16 and the 16 bytes in front of the
-// period are addressable; 2: anything else (short period / start of output) -> byte gather.
-__device__ __forceinline__ uint4 chunk_source(const uint8_t *pat, uint32_t rel, uint32_t offset, float inv, int mode)
+// period are addressable; 2: periodic at the very start of the output -> byte gather.
+// mode 3: period < 16: the period has been unrolled to 32 bytes in shared memory (ext), so a chunk
+// is the 16 bytes at its phase.
+__device__ __forceinline__ uint4 chunk_source(const uint8_t *pat, uint32_t rel, uint32_t offset, float inv, int mode,
+                                              const uint8_t *ext)
 {
     if (mode == 0) return load16_unaligned(pat + rel);
     uint32_t j = mod_period(rel, offset, inv);
+    if (mode == 3) return load16_unaligned(ext + j);
     if (mode == 1) {
         // a chunk is one contiguous run of the period (A), or its end followed by its start (A then B)
         const int t = (int)(offset - j);              // bytes left in this period, >= 1
@@ -389,7 +393,8 @@ __device__ __forceinline__ uint4 chunk_source(const uint8_t *pat, uint32_t rel, 
 // edge bytes and 16-byte chunks) are issued before the first store and the
 // match costs a single memory round trip.
 template <bool ADLER, int G>
-__device__ __forceinline__ void copy_match(const Grp<G> &g, OutState &o, unsigned length, unsigned offset)
+__device__ __forceinline__ void copy_match_part(const Grp<G> &g, OutState &o, unsigned length, unsigned offset,
+                                                uint8_t *ext)
 {
     constexpr int ER = (30 + G - 1) / G;     // rounds for up to 15 head + 15 tail bytes
     constexpr int BR = (16 + G - 1) / G;     // rounds for up to 16 chunks
@@ -415,7 +420,12 @@ __device__ __forceinline__ void copy_match(const Grp<G> &g, OutState &o, unsigne
     const uint32_t nedge = head + ((length - head) & 15u);
     const bool wrap = offset < length;
     const float inv = wrap ? __fdividef(1.f, (float)offset) : 0.f;
-    const int mode = !wrap ? 0 : (offset >= 16 && dpos - offset >= 20) ? 1 : 2;
+    const int mode = !wrap ? 0 : offset < 16 ? 3 : dpos - offset >= 20 ? 1 : 2;
+    if (mode == 3) {
+        // unroll the short period to 32 bytes in shared memory (one byte per lane per round)
+        for (uint32_t k = g.lane; k < 32; k += G) ext[k] = pat[k % offset];
+        g.sync();
+    }
     uint32_t eb[ER];
     uint4 cv[BR];
 #pragma unroll
@@ -430,7 +440,7 @@ __device__ __forceinline__ void copy_match(const Grp<G> &g, OutState &o, unsigne
 #pragma unroll
     for (int r = 0; r < BR; r++) {
         const uint32_t c = g.lane + r * G;
-        if (c < nbody) cv[r] = chunk_source(pat, head + 16 * c, offset, inv, mode);
+        if (c < nbody) cv[r] = chunk_source(pat, head + 16 * c, offset, inv, mode, ext);
     }
 #pragma unroll
     for (int r = 0; r < ER; r++) {
@@ -456,11 +466,30 @@ __device__ __forceinline__ void copy_match(const Grp<G> &g, OutState &o, unsigne
 #pragma unroll 1
     for (uint32_t c = g.lane + BR * G; c < nbody; c += G) {
         const uint32_t rel = head + 16 * c;
-        const uint4 v = chunk_source(pat, rel, offset, inv, mode);
+        const uint4 v = chunk_source(pat, rel, offset, inv, mode, ext);
         *reinterpret_cast<uint4 *>(base + dpos + rel) = v;
         adler_acc16<ADLER>(o, dpos + rel, v);
     }
     o.pos += length;
+}
+
+
+// A long periodic match that starts right behind its first period (e.g. a whole stream that is one
+// repeated record) cannot look back in front of the period; its first period(s) are written as a
+// separate part, after which the rest sees an ordinary periodic source.
+template <bool ADLER, int G>
+__device__ __forceinline__ void copy_match(const Grp<G> &g, OutState &o, unsigned length, unsigned offset,
+                                           uint8_t *ext)
+{
+    unsigned part = length;
+    if (offset >= 16 && o.pos - offset < 20 && length > 2 * offset + 64) part = offset >= 20 ? offset : 2 * offset;
+#pragma unroll 1
+    for (;;) {
+        copy_match_part<ADLER, G>(g, o, part, offset, ext);
+        length -= part;
+        if (length == 0) break;
+        part = length;
+    }
 }
 
 // ------------------------------------------------------------ block decoding
@@ -537,7 +566,7 @@ __device__ int decode_huffman_block(const Grp<G> &g, BitReader &br, OutState &o,
             }
         }
         make_valid<G>(g, o, o.pos + length + G);      // also covers the next literal flush
-        copy_match<ADLER, G>(g, o, length, offset);
+        copy_match<ADLER, G>(g, o, length, offset, reinterpret_cast<uint8_t *>(sm.cnt));
         if (ADLER) adler_fold(o);
     }
 }
