@@ -89,7 +89,7 @@ template <int FORMAT, int G>
 int launch_inflate_g(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
 {
     constexpr int groups = bdf::INF_THREADS / G;
-    const size_t smem = sizeof(bdf::InflateSmem) * groups;
+    const size_t smem = sizeof(bdf::InflateSmem<G>) * groups;
     int &bps = ctx->inflate_blocks_per_sm[FORMAT];
     if (bps == 0) {
         CK(cudaFuncSetAttribute(bdf::inflate_kernel<FORMAT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -111,7 +111,6 @@ int launch_inflate(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
 {
     switch (ctx->inflate_group) {
         case 32: return launch_inflate_g<FORMAT, 32>(ctx, a, s);
-        case 8: return launch_inflate_g<FORMAT, 8>(ctx, a, s);
         default: return launch_inflate_g<FORMAT, 16>(ctx, a, s);
     }
 }
@@ -142,7 +141,7 @@ int bdf_ctx_create(int device, bdf_ctx **out)
     ctx->device = device;
     if (const char *e = getenv("BDF_INFLATE_GROUP")) {
         int v = atoi(e);
-        if (v == 8 || v == 16 || v == 32) ctx->inflate_group = v;
+        if (v == 16 || v == 32) ctx->inflate_group = v;
     }
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);

@@ -40,13 +40,27 @@ struct HuffCode {            // canonical description used for build + long code
     uint16_t offs[16];       // index of the first symbol of each length in sorted[]
 };
 
+// Scratch of the table builder.  rows: one row of 16 per-length counters per lane (u16, padded to a
+// 9-word stride so that the rows of a group fall into different banks); big_*: direct-table fills
+// of 32 slots or more, deferred so that the whole group can do them together.
+constexpr int ROW_STRIDE = 18;
+template <int G>
+struct BuildScratch {
+    uint32_t cnt[16];                  // also the 32-byte period buffer of copy_match_part (mode 3)
+    uint32_t big_e[16];
+    uint16_t big_r[16];
+    uint32_t nbig;
+    uint16_t rows[G * ROW_STRIDE];
+};
+
+template <int G>
 struct __align__(16) InflateSmem {     // one per lane group
     uint32_t lit_tab[1 << LT_BITS];
     uint32_t off_tab[1 << OT_BITS];
     uint16_t lit_sorted[288];
     uint16_t off_sorted[32];
     HuffCode lit_code, off_code;
-    uint32_t cnt[16];                  // scratch: length histogram / running ranks
+    BuildScratch<G> bs;
     uint8_t lens[320 + 8];
 };
 
@@ -150,37 +164,55 @@ __device__ __forceinline__ uint32_t make_entry(unsigned sym, unsigned l)
 // Returns false (uniformly over the group) for code sets the reference
 // rejects: over-subscribed, or incomplete other than "no codes" / "one 1-bit
 // code" (src/decompress/mod.rs:1365-1383).
+//
+// Lane j owns the symbols [j*per, (j+1)*per) and, as "length owner", the code length j.  Pass 1:
+// every lane counts the lengths of its symbols into its row.  The length owners then turn their
+// column into exclusive prefixes (= canonical rank of a lane's first symbol of that length) and
+// derive first codeword / sorted offset of their length with two shuffle scans.  Pass 2: every
+// lane walks its symbols again; rank -> codeword -> the symbol writes its own table slots.  No
+// group synchronisation inside either pass.
 template <int KIND, int TBITS, int G>
 __device__ bool build_code(const Grp<G> &g, const uint8_t *lens, unsigned nsyms, uint32_t *tab,
-                           uint16_t *sorted, HuffCode &hc, uint32_t *cnt)
+                           uint16_t *sorted, HuffCode &hc, BuildScratch<G> &bs)
 {
-    for (unsigned i = g.lane; i < 16; i += G) cnt[i] = 0;
-    g.sync();
-    for (unsigned s = g.lane; s < nsyms; s += G) {
-        unsigned l = lens[s];
-        if (l) atomicAdd(&cnt[l], 1u);
+    static_assert(G >= 16, "one length owner per code length");
+    constexpr unsigned BIG = TBITS >= 5 ? TBITS - 5 : 0;      // codewords of <= BIG bits fill >= 32 slots
+    uint16_t *row = bs.rows + g.lane * ROW_STRIDE;
+    {
+        uint32_t *rw = reinterpret_cast<uint32_t *>(row);      // 36-byte stride: 4-byte aligned
+#pragma unroll
+        for (int k = 0; k < 8; k++) rw[k] = 0;
     }
+    const unsigned per = (nsyms + G - 1) / G;
+    const unsigned s0 = g.lane * per;
+    const unsigned s1 = s0 + per < nsyms ? s0 + per : nsyms;
+    for (unsigned s = s0; s < s1; s++) row[lens[s]]++;
+    if (g.lane == 0) bs.nbig = 0;
     g.sync();
-    // every lane derives the same canonical description; lane (l mod G) stores entry l
-    uint32_t used = 0, code = 0, run = 0, total = 0;
-    const uint32_t c1 = cnt[1];
-    uint32_t cl[16];
-#pragma unroll
-    for (unsigned l = 1; l <= 15; l++) cl[l] = cnt[l];
-    g.sync();
-#pragma unroll
-    for (unsigned l = 1; l <= 15; l++) {
-        const uint32_t c = cl[l];
-        used += c << (15 - l);
-        if ((l & (unsigned)(G - 1)) == g.lane) {
-            hc.first[l] = (uint16_t)code;
-            hc.count[l] = (uint16_t)c;
-            hc.offs[l] = (uint16_t)run;
-            cnt[l] = 0;              // becomes the running rank per length
+    const unsigned L = g.lane;
+    const bool owner = L >= 1 && L < 16;
+    uint32_t tot = 0;
+    if (owner) {
+#pragma unroll 4
+        for (int j = 0; j < G; j++) {
+            const uint32_t c = bs.rows[j * ROW_STRIDE + L];
+            bs.rows[j * ROW_STRIDE + L] = (uint16_t)tot;
+            tot += c;
         }
-        code = (code + c) << 1;
-        run += c;
-        total += c;
+    }
+    // inclusive scans over the lengths: Kraft sum in units of 2^-15, and symbol count
+    const uint32_t v = owner ? tot << (15 - L) : 0;
+    uint32_t iv = v, ic = tot;
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) {
+        const uint32_t x = g.shfl_up(iv, d), y = g.shfl_up(ic, d);
+        if (g.lane >= (unsigned)d) { iv += x; ic += y; }
+    }
+    const uint32_t used = g.shfl(iv, 15), total = g.shfl(ic, 15), c1 = g.shfl(tot, 1);
+    if (owner) {
+        hc.first[L] = (uint16_t)((iv - v) >> (15 - L));
+        hc.count[L] = (uint16_t)tot;
+        hc.offs[L] = (uint16_t)(ic - tot);
     }
     g.sync();
     if (used > (1u << 15)) return false;
@@ -201,31 +233,36 @@ __device__ bool build_code(const Grp<G> &g, const uint8_t *lens, unsigned nsyms,
         g.sync();
         return true;
     }
-    // One pass over the symbols, G at a time: canonical rank within the length
-    // (match.any), position in sorted[] (needed for codewords longer than the
-    // table), and the direct-table slots of the symbol: a codeword of l <= TBITS
-    // bits owns the 2^(TBITS-l) slots whose low l bits are its reversed bits;
-    // a longer codeword marks its TBITS-bit prefix slot with 0.
-    for (unsigned base = 0; base < nsyms; base += G) {
-        const unsigned s = base + g.lane;
-        const unsigned l = s < nsyms ? lens[s] : 0;
-        const unsigned peers = g.match_any(l);
-        const unsigned rank = __popc(peers & g.lt_mask());
-        if (l) {
-            const unsigned idx = cnt[l] + rank;
-            sorted[hc.offs[l] + idx] = (uint16_t)s;
-            const unsigned rev = __brev((unsigned)hc.first[l] + idx) >> (32 - l);
-            if (l <= TBITS) {
-                const uint32_t e = make_entry<KIND>(s, l);
-                for (unsigned i = rev; i < (1u << TBITS); i += 1u << l) tab[i] = e;
+    // A codeword of l <= TBITS bits owns the 2^(TBITS-l) slots whose low l bits are its reversed
+    // bits; a longer codeword marks its TBITS-bit prefix slot with 0 (-> canonical search).
+    for (unsigned s = s0; s < s1; s++) {
+        const unsigned l = lens[s];
+        if (l == 0) continue;
+        const unsigned rank = row[l];
+        row[l] = (uint16_t)(rank + 1);
+        sorted[hc.offs[l] + rank] = (uint16_t)s;
+        const unsigned rev = __brev((unsigned)hc.first[l] + rank) >> (32 - l);
+        if (l <= TBITS) {
+            const uint32_t e = make_entry<KIND>(s, l);
+            if (l <= BIG) {
+                const unsigned k = atomicAdd(&bs.nbig, 1u);    // at most 2^BIG <= 16 such codewords
+                bs.big_e[k] = e;
+                bs.big_r[k] = (uint16_t)(rev | l << 12);
             } else {
-                tab[rev & ((1u << TBITS) - 1u)] = 0;
+                for (unsigned i = rev; i < (1u << TBITS); i += 1u << l) tab[i] = e;
             }
+        } else {
+            tab[rev & ((1u << TBITS) - 1u)] = 0;
         }
-        g.sync();
-        if (l && (peers >> g.lane) == 1u) cnt[l] += __popc(peers);   // highest lane of the rank group
-        g.sync();
     }
+    g.sync();
+    const unsigned nbig = bs.nbig;
+    for (unsigned k = 0; k < nbig; k++) {
+        const uint32_t e = bs.big_e[k];
+        const unsigned r = bs.big_r[k], l = r >> 12;
+        for (unsigned i = (r & 0xFFFu) + (g.lane << l); i < (1u << TBITS); i += (unsigned)G << l) tab[i] = e;
+    }
+    g.sync();
     return true;
 }
 
@@ -474,21 +511,97 @@ __device__ __forceinline__ void copy_match_part(const Grp<G> &g, OutState &o, un
 }
 
 
-// A long periodic match that starts right behind its first period (e.g. a whole stream that is one
-// repeated record) cannot look back in front of the period; its first period(s) are written as a
-// separate part, after which the rest sees an ordinary periodic source.
+// Whole match.  Three things happen here:
+//  * Parts.  The generic copy works on parts of at most COPY_PART bytes, each preceded by the
+//    zero-fill of its own range only: filling all of a 64 KiB coalesced match ahead of the copy
+//    would push the zeroes out to DRAM before they are overwritten (measured: DRAM writes 2x).
+//    A long periodic match that starts right behind its first period (a stream that is one
+//    repeated record) cannot look back in front of the period; its first period(s) are their own part.
+//  * Long periodic matches (corpus A: one 65 KiB match of period 100 per stream).  Bytes repeat at
+//    every multiple of the period, so after a lead-in of D bytes — D a multiple of lcm(period, 16)
+//    and at least LONG_UNROLL group steps — the rest is out[i] = out[i - D] with BOTH sides 16-byte
+//    aligned: one LDG.128 + one STG.128 per chunk, no realignment, no modulo, and whole sectors
+//    written without any zero-fill.  Sources lie >= LONG_UNROLL steps behind, so LONG_UNROLL
+//    loads are in flight per lane before the first store of a step.
+//  * Adler-32 of the aligned part is kept as (sum s, sum w, sum t*s) over the lane's chunks and
+//    folded into the 64-bit position-weighted sum once.
+constexpr uint32_t COPY_PART = 4096;
+constexpr int LONG_UNROLL = 4;
+constexpr uint32_t LONG_D0_MAX = 4096;
 template <bool ADLER, int G>
 __device__ __forceinline__ void copy_match(const Grp<G> &g, OutState &o, unsigned length, unsigned offset,
                                            uint8_t *ext)
 {
-    unsigned part = length;
-    if (offset >= 16 && o.pos - offset < 20 && length > 2 * offset + 64) part = offset >= 20 ? offset : 2 * offset;
+    constexpr uint32_t SPAN = 16u * G * LONG_UNROLL;      // bytes one unrolled group step writes
+    uint32_t lead = length, dist = 0;
+    if (length >= 4 * SPAN && offset < length) {
+        const uint32_t tz = __ffs(offset) - 1;
+        const uint32_t d0 = offset << (4u - (tz < 4u ? tz : 4u));         // lcm(offset, 16)
+        if (d0 <= LONG_D0_MAX) {
+            const uint32_t d = d0 * ((SPAN + d0 - 1) / d0);
+            const uint32_t l1 = d + ((16u - (uint32_t)(reinterpret_cast<uintptr_t>(o.out + o.pos + d) & 15u)) & 15u);
+            if (length >= l1 + 2 * SPAN) { lead = l1; dist = d; }
+        }
+    }
+    uint32_t rem = lead;
 #pragma unroll 1
-    for (;;) {
+    while (rem) {
+        uint32_t part = rem < COPY_PART ? rem : COPY_PART;
+        if (offset >= 16 && o.pos - offset < 20 && rem > 2 * offset + 64) part = offset >= 20 ? offset : 2 * offset;
+        make_valid<G>(g, o, o.pos + part + G);        // + G: also covers the next literal flush
         copy_match_part<ADLER, G>(g, o, part, offset, ext);
-        length -= part;
-        if (length == 0) break;
-        part = length;
+        rem -= part;
+    }
+    if (dist) {
+        g.sync();
+        const uint32_t p2 = o.pos, n2 = length - lead;
+        const uint32_t nch = n2 >> 4;
+        uint4 *d16 = reinterpret_cast<uint4 *>(o.out + p2);
+        const uint4 *s16 = reinterpret_cast<const uint4 *>(o.out + p2 - dist);
+        uint32_t S = 0, W = 0, T = 0, t = 0, c = g.lane;
+        // group-uniform trip count (the step ends in a group barrier): whole steps only
+#pragma unroll 1
+        for (uint32_t cb = 0; cb + LONG_UNROLL * G <= nch; cb += LONG_UNROLL * G, c += LONG_UNROLL * G, t += LONG_UNROLL) {
+            uint4 v[LONG_UNROLL];
+#pragma unroll
+            for (int u = 0; u < LONG_UNROLL; u++) v[u] = s16[c + u * G];
+#pragma unroll
+            for (int u = 0; u < LONG_UNROLL; u++) {
+                d16[c + u * G] = v[u];
+                if (ADLER) {
+                    const uint32_t sx = __dp4a(v[u].x, 0x01010101u, __dp4a(v[u].y, 0x01010101u, __dp4a(v[u].z, 0x01010101u, __dp4a(v[u].w, 0x01010101u, 0u))));
+                    W = __dp4a(v[u].x, 0x03020100u, __dp4a(v[u].y, 0x07060504u, __dp4a(v[u].z, 0x0B0A0908u, __dp4a(v[u].w, 0x0F0E0D0Cu, W))));
+                    S += sx;
+                    T += (t + u) * sx;
+                }
+            }
+            g.sync();      // the next step's sources may be this step's chunks
+        }
+#pragma unroll 1
+        for (; c < nch; c += G, t++) {                    // < LONG_UNROLL leftover chunks per lane
+            const uint4 x = s16[c];
+            d16[c] = x;
+            if (ADLER) {
+                const uint32_t sx = __dp4a(x.x, 0x01010101u, __dp4a(x.y, 0x01010101u, __dp4a(x.z, 0x01010101u, __dp4a(x.w, 0x01010101u, 0u))));
+                W = __dp4a(x.x, 0x03020100u, __dp4a(x.y, 0x07060504u, __dp4a(x.z, 0x0B0A0908u, __dp4a(x.w, 0x0F0E0D0Cu, W))));
+                S += sx;
+                T += t * sx;
+            }
+        }
+        if (ADLER) {
+            // chunk (lane + G*t) starts at output index p2 + 16*(lane + G*t)
+            o.sumA += S;
+            o.sumB += (uint64_t)p2 * S + 16ull * ((uint64_t)g.lane * S + (uint64_t)G * T) + W;
+        }
+        const uint32_t tail = n2 & 15u;
+        g.sync();                                         // a tail source can be one of the leftover chunks
+        if (g.lane < tail) {
+            const uint32_t i = p2 + 16 * nch + g.lane;
+            const uint32_t bb = o.out[i - dist];
+            o.out[i] = (uint8_t)bb;
+            adler_acc1<ADLER>(o, i, bb);
+        }
+        o.pos += n2;
     }
 }
 
@@ -506,12 +619,15 @@ constexpr uint32_t COALESCE_MAX = BDF_COALESCE_MAX;
 constexpr uint32_t COALESCE_MIN_LEN = 64;
 
 template <bool ADLER, int G>
-__device__ int decode_huffman_block(const Grp<G> &g, BitReader &br, OutState &o, InflateSmem &sm)
+__device__ int decode_huffman_block(const Grp<G> &g, BitReader &br, OutState &o, InflateSmem<G> &sm)
 {
     for (;;) {
         // more than two zero-fill words loaded: the stream ended inside this block
         if (br.widx > br.nwords + 2) return BDF_SHORT_INPUT;
         br.refill();
+        const uint32_t tok_lo = (uint32_t)br.buf;      // >= 33 valid bits: the next 32 bits of the stream
+        const int32_t tok_left = br.left;
+        const uint32_t tok_widx = br.widx;
         uint32_t e = sm.lit_tab[br.peek(LT_BITS)];
         if ((e & 31u) == 0) {
             e = decode_long<CODE_LITLEN, LT_BITS>(br.peek(15), sm.lit_sorted, sm.lit_code);
@@ -532,7 +648,7 @@ __device__ int decode_huffman_block(const Grp<G> &g, BitReader &br, OutState &o,
             return br.overrun() ? BDF_SHORT_INPUT : BDF_OK;
         }
         unsigned length = (e >> 16) + br.take((e >> 5) & 15u);
-        br.refill();
+        br.refill();                                   // appends above `left`: consumed-bit accounting is unchanged
         uint32_t f = sm.off_tab[br.peek(OT_BITS)];
         if ((f & 31u) == 0) {
             f = decode_long<CODE_OFFSET, OT_BITS>(br.peek(15), sm.off_sorted, sm.off_code);
@@ -544,6 +660,26 @@ __device__ int decode_huffman_block(const Grp<G> &g, BitReader &br, OutState &o,
         if (offset > o.pos) return BDF_BAD_DATA;
         if (o.pos + length > o.cap) return BDF_INSUFFICIENT_SPACE;
         if (length >= COALESCE_MIN_LEN && COALESCE_MAX) {
+            // (a) The same match again: Huffman decoding is a function of the bits, so if the next
+            // bits equal the bits of the token just decoded they decode to the same (length,
+            // offset).  Run-length / periodic data is hundreds of identical tokens in a row; each
+            // costs one compare here instead of two table look-ups.
+            const uint32_t tok_bits = (uint32_t)(tok_left - br.left) + 32u * (br.widx - tok_widx);
+            if (tok_bits <= 32u) {
+                const uint32_t tmask = 0xFFFFFFFFu >> (32u - tok_bits);
+                const uint32_t tpat = tok_lo & tmask;
+                const unsigned len1 = length;
+#pragma unroll 1
+                for (;;) {
+                    if (br.widx > br.nwords + 2) break;
+                    br.refill();
+                    if ((((uint32_t)br.buf ^ tpat) & tmask) != 0) break;
+                    if (length + len1 > COALESCE_MAX || o.pos + length + len1 > o.cap) break;
+                    br.drop(tok_bits);
+                    length += len1;
+                }
+            }
+            // (b) another match with the same offset but a different length (the last one of a run)
 #pragma unroll 1
             for (;;) {
                 BitReader t = br;
@@ -565,15 +701,14 @@ __device__ int decode_huffman_block(const Grp<G> &g, BitReader &br, OutState &o,
                 length += len2;
             }
         }
-        make_valid<G>(g, o, o.pos + length + G);      // also covers the next literal flush
-        copy_match<ADLER, G>(g, o, length, offset, reinterpret_cast<uint8_t *>(sm.cnt));
+        copy_match<ADLER, G>(g, o, length, offset, reinterpret_cast<uint8_t *>(sm.bs.cnt));
         if (ADLER) adler_fold(o);
     }
 }
 
 // read_dynamic_huffman_header, src/decompress/mod.rs:403-507
 template <int G>
-__device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, InflateSmem &sm)
+__device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, InflateSmem<G> &sm)
 {
     br.refill();
     const unsigned nlit = 257 + br.take(5);
@@ -602,7 +737,7 @@ __device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, InflateSmem &
     }
     if (br.overrun()) return BDF_SHORT_INPUT;
     uint32_t *pre_tab = sm.off_tab;
-    if (!build_code<CODE_PRECODE, PT_BITS, G>(g, pre_lens, 19, pre_tab, sm.off_sorted, sm.off_code, sm.cnt))
+    if (!build_code<CODE_PRECODE, PT_BITS, G>(g, pre_lens, 19, pre_tab, sm.off_sorted, sm.off_code, sm.bs))
         return BDF_BAD_DATA;
     // run-length decode of the litlen + offset code lengths (group-uniform)
     const unsigned total = nlit + noff;
@@ -637,26 +772,26 @@ __device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, InflateSmem &
     }
     if (br.overrun()) return BDF_SHORT_INPUT;
     g.sync();
-    if (!build_code<CODE_OFFSET, OT_BITS, G>(g, sm.lens + nlit, noff, sm.off_tab, sm.off_sorted, sm.off_code, sm.cnt))
+    if (!build_code<CODE_OFFSET, OT_BITS, G>(g, sm.lens + nlit, noff, sm.off_tab, sm.off_sorted, sm.off_code, sm.bs))
         return BDF_BAD_DATA;
-    if (!build_code<CODE_LITLEN, LT_BITS, G>(g, sm.lens, nlit, sm.lit_tab, sm.lit_sorted, sm.lit_code, sm.cnt))
+    if (!build_code<CODE_LITLEN, LT_BITS, G>(g, sm.lens, nlit, sm.lit_tab, sm.lit_sorted, sm.lit_code, sm.bs))
         return BDF_BAD_DATA;
     return BDF_OK;
 }
 
 template <int G>
-__device__ void load_static_codes(const Grp<G> &g, InflateSmem &sm)
+__device__ void load_static_codes(const Grp<G> &g, InflateSmem<G> &sm)
 {
     for (unsigned s = g.lane; s < 320; s += G)
         sm.lens[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : s < 288 ? 8 : 5;
     g.sync();
-    build_code<CODE_OFFSET, OT_BITS, G>(g, sm.lens + 288, 32, sm.off_tab, sm.off_sorted, sm.off_code, sm.cnt);
-    build_code<CODE_LITLEN, LT_BITS, G>(g, sm.lens, 288, sm.lit_tab, sm.lit_sorted, sm.lit_code, sm.cnt);
+    build_code<CODE_OFFSET, OT_BITS, G>(g, sm.lens + 288, 32, sm.off_tab, sm.off_sorted, sm.off_code, sm.bs);
+    build_code<CODE_LITLEN, LT_BITS, G>(g, sm.lens, 288, sm.lit_tab, sm.lit_sorted, sm.lit_code, sm.bs);
 }
 
 // Raw DEFLATE stream [p, p+len) -> o; returns status, *used = bytes consumed.
 template <bool ADLER, int G>
-__device__ int inflate_stream(const Grp<G> &g, const uint8_t *p, uint32_t len, OutState &o, InflateSmem &sm,
+__device__ int inflate_stream(const Grp<G> &g, const uint8_t *p, uint32_t len, OutState &o, InflateSmem<G> &sm,
                               uint32_t *used)
 {
     BitReader br;
@@ -778,24 +913,30 @@ struct InflateArgs {
 constexpr int INF_THREADS = 64;     // threads per CTA; 64 / G lane groups = streams in flight per CTA
 
 template <int FORMAT, int G>
-__global__ void __launch_bounds__(INF_THREADS, G >= 16 ? 14 : 8)
+__global__ void __launch_bounds__(INF_THREADS, 12)
 inflate_kernel(InflateArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_crc[FORMAT == BDF_GZIP ? 4 : 1][256];
     __shared__ uint32_t s_x2n[32];
-    InflateSmem &sm = reinterpret_cast<InflateSmem *>(smem_raw)[threadIdx.x / G];
+    InflateSmem<G> &sm = reinterpret_cast<InflateSmem<G> *>(smem_raw)[threadIdx.x / G];
     const Grp<G> g;
     if (FORMAT == BDF_GZIP) {
         for (unsigned i = threadIdx.x; i < 1024; i += blockDim.x) s_crc[i >> 8][i & 255] = g_crc_tables.slice[i >> 8][i & 255];
         if (threadIdx.x < 32) s_x2n[threadIdx.x] = g_crc_tables.x2n[threadIdx.x];
         __syncthreads();
     }
+    // The groups of a warp take their streams TOGETHER: streams of one batch tend to look alike, and
+    // groups that start together stay in lock-step (one instruction stream for 32/G streams);
+    // groups that fetched on their own would drift apart for good and execute one after the other.
+    constexpr unsigned GPW = 32 / G;
     for (;;) {
         unsigned long long idx = 0;
-        if (g.lane == 0) idx = atomicAdd(a.work_counter, 1ull);
-        idx = g.shfl(idx, 0);
+        if (lane_id() == 0) idx = atomicAdd(a.work_counter, (unsigned long long)GPW);
+        idx = __shfl_sync(BDF_FULL_MASK, idx, 0);
         if (idx >= a.n) break;
+        idx += lane_id() / G;
+        if (idx < a.n) {
         const uint8_t *p = a.in + a.in_off[idx];
         const uint64_t len64 = a.in_off[idx + 1] - a.in_off[idx];
         const uint64_t cap64 = a.max_out[idx];
@@ -869,7 +1010,8 @@ inflate_kernel(InflateArgs a)
             a.out_size[idx] = st == BDF_OK ? o.pos : 0;
             if (a.checksum) a.checksum[idx] = st == BDF_OK ? sum : 0;
         }
-        g.sync();
+        }
+        __syncwarp();
     }
 }
 
