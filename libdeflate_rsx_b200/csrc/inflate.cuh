@@ -517,31 +517,34 @@ __device__ __forceinline__ void copy_match_part(const Grp<G> &g, OutState &o, un
 //    would push the zeroes out to DRAM before they are overwritten (measured: DRAM writes 2x).
 //    A long periodic match that starts right behind its first period (a stream that is one
 //    repeated record) cannot look back in front of the period; its first period(s) are their own part.
-//  * Long periodic matches (corpus A: one 65 KiB match of period 100 per stream).  Bytes repeat at
-//    every multiple of the period, so after a lead-in of D bytes — D a multiple of lcm(period, 16)
-//    and at least LONG_UNROLL group steps — the rest is out[i] = out[i - D] with BOTH sides 16-byte
-//    aligned: one LDG.128 + one STG.128 per chunk, no realignment, no modulo, and whole sectors
-//    written without any zero-fill.  Sources lie >= LONG_UNROLL steps behind, so LONG_UNROLL
-//    loads are in flight per lane before the first store of a step.
-//  * Adler-32 of the aligned part is kept as (sum s, sum w, sum t*s) over the lane's chunks and
-//    folded into the 64-bit position-weighted sum once.
+//  * Long periodic matches (corpus A: one 65 KiB match of period 100 per stream; a run of zeroes
+//    is period 1).  After a lead-in that ends on a 16-byte boundary and covers D = lcm(period, 16)
+//    bytes, the rest of the match is the D bytes in front of it over and over, chunk c being
+//    chunk (c mod D/16) of that block.  The block never changes while the match is written, so
+//    the loop has no dependences at all: one L1-resident LDG.128 and one STG.128 per chunk, no
+//    realignment, no barrier, whole sectors written (no zero-fill needed).
+//  * The Adler-32 contribution of that part follows from the sums over ONE block (and over the
+//    partial last one): out[p2 + m*D + k] = blk[k], so sum i*b is a polynomial in the block sums.
 constexpr uint32_t COPY_PART = 4096;
-constexpr int LONG_UNROLL = 4;
-constexpr uint32_t LONG_D0_MAX = 4096;
+constexpr uint32_t LONG_D_MAX = 4096;
+constexpr uint32_t LONG_MIN_BODY = 512;
+
+// bytes [0, n) of w (n may be <= 0 or >= 4)
+__device__ __forceinline__ uint32_t keep_low_bytes(uint32_t w, int n)
+{
+    return n <= 0 ? 0u : n >= 4 ? w : w & ((1u << (8 * n)) - 1u);
+}
+
 template <bool ADLER, int G>
 __device__ __forceinline__ void copy_match(const Grp<G> &g, OutState &o, unsigned length, unsigned offset,
                                            uint8_t *ext)
 {
-    constexpr uint32_t SPAN = 16u * G * LONG_UNROLL;      // bytes one unrolled group step writes
     uint32_t lead = length, dist = 0;
-    if (length >= 4 * SPAN && offset < length) {
+    if (length >= 2 * LONG_MIN_BODY && offset < length) {
         const uint32_t tz = __ffs(offset) - 1;
-        const uint32_t d0 = offset << (4u - (tz < 4u ? tz : 4u));         // lcm(offset, 16)
-        if (d0 <= LONG_D0_MAX) {
-            const uint32_t d = d0 * ((SPAN + d0 - 1) / d0);
-            const uint32_t l1 = d + ((16u - (uint32_t)(reinterpret_cast<uintptr_t>(o.out + o.pos + d) & 15u)) & 15u);
-            if (length >= l1 + 2 * SPAN) { lead = l1; dist = d; }
-        }
+        const uint32_t d = offset << (4u - (tz < 4u ? tz : 4u));          // lcm(offset, 16)
+        const uint32_t l1 = d + ((16u - (uint32_t)(reinterpret_cast<uintptr_t>(o.out + o.pos + d) & 15u)) & 15u);
+        if (d <= LONG_D_MAX && length >= l1 + LONG_MIN_BODY) { lead = l1; dist = d; }
     }
     uint32_t rem = lead;
 #pragma unroll 1
@@ -553,53 +556,75 @@ __device__ __forceinline__ void copy_match(const Grp<G> &g, OutState &o, unsigne
         rem -= part;
     }
     if (dist) {
-        g.sync();
+        g.sync();                                     // the block was written by all lanes of the group
         const uint32_t p2 = o.pos, n2 = length - lead;
-        const uint32_t nch = n2 >> 4;
+        const uint32_t nch = n2 >> 4, nblk = dist >> 4;
         uint4 *d16 = reinterpret_cast<uint4 *>(o.out + p2);
-        const uint4 *s16 = reinterpret_cast<const uint4 *>(o.out + p2 - dist);
-        uint32_t S = 0, W = 0, T = 0, t = 0, c = g.lane;
-        // group-uniform trip count (the step ends in a group barrier): whole steps only
+        const uint4 *blk = reinterpret_cast<const uint4 *>(o.out + p2 - dist);
+        {
+            // loads of four steps first: the compiler cannot know that the stores never hit the block
+            uint32_t j = g.lane % nblk, c = g.lane;
+            const uint32_t gs = (uint32_t)G % nblk;
 #pragma unroll 1
-        for (uint32_t cb = 0; cb + LONG_UNROLL * G <= nch; cb += LONG_UNROLL * G, c += LONG_UNROLL * G, t += LONG_UNROLL) {
-            uint4 v[LONG_UNROLL];
+            for (; c + 3 * G < nch; c += 4 * G) {
+                uint4 v[4];
 #pragma unroll
-            for (int u = 0; u < LONG_UNROLL; u++) v[u] = s16[c + u * G];
-#pragma unroll
-            for (int u = 0; u < LONG_UNROLL; u++) {
-                d16[c + u * G] = v[u];
-                if (ADLER) {
-                    const uint32_t sx = __dp4a(v[u].x, 0x01010101u, __dp4a(v[u].y, 0x01010101u, __dp4a(v[u].z, 0x01010101u, __dp4a(v[u].w, 0x01010101u, 0u))));
-                    W = __dp4a(v[u].x, 0x03020100u, __dp4a(v[u].y, 0x07060504u, __dp4a(v[u].z, 0x0B0A0908u, __dp4a(v[u].w, 0x0F0E0D0Cu, W))));
-                    S += sx;
-                    T += (t + u) * sx;
+                for (int u = 0; u < 4; u++) {
+                    v[u] = blk[j];
+                    j += gs;
+                    if (j >= nblk) j -= nblk;
                 }
+#pragma unroll
+                for (int u = 0; u < 4; u++) d16[c + u * G] = v[u];
             }
-            g.sync();      // the next step's sources may be this step's chunks
-        }
 #pragma unroll 1
-        for (; c < nch; c += G, t++) {                    // < LONG_UNROLL leftover chunks per lane
-            const uint4 x = s16[c];
-            d16[c] = x;
-            if (ADLER) {
-                const uint32_t sx = __dp4a(x.x, 0x01010101u, __dp4a(x.y, 0x01010101u, __dp4a(x.z, 0x01010101u, __dp4a(x.w, 0x01010101u, 0u))));
-                W = __dp4a(x.x, 0x03020100u, __dp4a(x.y, 0x07060504u, __dp4a(x.z, 0x0B0A0908u, __dp4a(x.w, 0x0F0E0D0Cu, W))));
-                S += sx;
-                T += t * sx;
+            for (; c < nch; c += G) {
+                d16[c] = blk[j];
+                j += gs;
+                if (j >= nblk) j -= nblk;
             }
-        }
-        if (ADLER) {
-            // chunk (lane + G*t) starts at output index p2 + 16*(lane + G*t)
-            o.sumA += S;
-            o.sumB += (uint64_t)p2 * S + 16ull * ((uint64_t)g.lane * S + (uint64_t)G * T) + W;
         }
         const uint32_t tail = n2 & 15u;
-        g.sync();                                         // a tail source can be one of the leftover chunks
-        if (g.lane < tail) {
-            const uint32_t i = p2 + 16 * nch + g.lane;
-            const uint32_t bb = o.out[i - dist];
-            o.out[i] = (uint8_t)bb;
-            adler_acc1<ADLER>(o, i, bb);
+        if (g.lane < tail)
+            o.out[p2 + 16 * nch + g.lane] = reinterpret_cast<const uint8_t *>(blk)[16 * (nch % nblk) + g.lane];
+        if (ADLER) {
+            const uint32_t q = n2 / dist, r = n2 - q * dist;
+            // block sums: SD = sum blk[k], WD = sum k*blk[k]; SR, WR the same over k < r
+            uint32_t SD = 0, WD = 0, SR = 0, WR = 0;
+            for (uint32_t k = g.lane; k < nblk; k += G) {
+                const uint4 x = blk[k];
+                const uint32_t sx = __dp4a(x.x, 0x01010101u, __dp4a(x.y, 0x01010101u, __dp4a(x.z, 0x01010101u, __dp4a(x.w, 0x01010101u, 0u))));
+                const uint32_t wx = 16u * k * sx + __dp4a(x.x, 0x03020100u, __dp4a(x.y, 0x07060504u, __dp4a(x.z, 0x0B0A0908u, __dp4a(x.w, 0x0F0E0D0Cu, 0u))));
+                SD += sx;
+                WD += wx;
+                if (k < (r >> 4)) { SR += sx; WR += wx; }
+            }
+            if ((r & 15u) && g.lane == 0) {           // the chunk the remainder ends in
+                const uint32_t k = r >> 4;
+                const int nb = (int)(r & 15u);
+                uint4 x = blk[k];
+                x.x = keep_low_bytes(x.x, nb); x.y = keep_low_bytes(x.y, nb - 4);
+                x.z = keep_low_bytes(x.z, nb - 8); x.w = keep_low_bytes(x.w, nb - 12);
+                const uint32_t sx = __dp4a(x.x, 0x01010101u, __dp4a(x.y, 0x01010101u, __dp4a(x.z, 0x01010101u, __dp4a(x.w, 0x01010101u, 0u))));
+                SR += sx;
+                WR += 16u * k * sx + __dp4a(x.x, 0x03020100u, __dp4a(x.y, 0x07060504u, __dp4a(x.z, 0x0B0A0908u, __dp4a(x.w, 0x0F0E0D0Cu, 0u))));
+            }
+            SD %= 65521u; WD %= 65521u; SR %= 65521u; WR %= 65521u;
+#pragma unroll
+            for (int sft = G / 2; sft > 0; sft >>= 1) {
+                SD += g.shfl_xor(SD, sft); WD += g.shfl_xor(WD, sft);
+                SR += g.shfl_xor(SR, sft); WR += g.shfl_xor(WR, sft);
+            }
+            if (g.lane == 0) {
+                // sum over m < q, k < D of (p2 + m*D + k) blk[k]  +  sum over k < r of (p2 + q*D + k) blk[k]
+                const uint64_t M = 65521u;
+                const uint64_t sd = SD % M, wd = WD % M, sr = SR % M, wr = WR % M;
+                const uint64_t qm = q % M, pm = p2 % M, dm = dist % M;
+                const uint64_t tri = ((uint64_t)q * (q - (q ? 1u : 0u)) / 2u) % M;
+                uint64_t db = qm * pm % M * sd + dm * sd % M * tri + qm * wd + (pm + qm * dm) % M * sr + wr;
+                o.sumA += (uint32_t)((qm * sd + sr) % M);
+                o.sumB += db % M;
+            }
         }
         o.pos += n2;
     }
@@ -669,6 +694,23 @@ __device__ int decode_huffman_block(const Grp<G> &g, BitReader &br, OutState &o,
                 const uint32_t tmask = 0xFFFFFFFFu >> (32u - tok_bits);
                 const uint32_t tpat = tok_lo & tmask;
                 const unsigned len1 = length;
+                // several tokens per compare while they fit into the 32 bits a refill guarantees
+                const uint32_t nrep = 32u / tok_bits;
+                if (nrep >= 2) {
+                    uint32_t rpat = tpat;
+                    for (uint32_t k = 1; k < nrep; k++) rpat |= tpat << (k * tok_bits);
+                    const uint32_t rbits = nrep * tok_bits, rmask = 0xFFFFFFFFu >> (32u - rbits);
+                    const uint32_t rlen = nrep * len1;
+#pragma unroll 1
+                    for (;;) {
+                        if (br.widx > br.nwords + 2) break;
+                        br.refill();
+                        if ((((uint32_t)br.buf ^ rpat) & rmask) != 0) break;
+                        if (length + rlen > COALESCE_MAX || o.pos + length + rlen > o.cap) break;
+                        br.drop(rbits);
+                        length += rlen;
+                    }
+                }
 #pragma unroll 1
                 for (;;) {
                     if (br.widx > br.nwords + 2) break;
