@@ -22,6 +22,7 @@
 // from the bytes as they are written (position-weighted partial sums per
 // lane, dp4a), so the zlib path never re-reads its output.
 #pragma once
+#include <cstddef>
 #include "common.cuh"
 
 namespace bdf {
@@ -31,8 +32,9 @@ constexpr int OT_BITS = 7;    // offset direct-table bits (the precode table, 7 
 constexpr int PT_BITS = 7;    // precode direct-table bits
 
 // Table entry (u32): [4:0] codeword bits (0 = longer than the table),
-// [8:5] extra bits, [10:9] kind, [31:16] literal / base value.
+// [8:5] extra bits, [10:9] kind, [15] literal, [31:16] literal / base value.
 constexpr uint32_t K_LIT = 0u << 9, K_BASE = 1u << 9, K_EOB = 2u << 9, K_MASK = 3u << 9;
+constexpr uint32_t LITFLAG = 1u << 15;    // set in literal entries only: one test selects the literal fast path
 
 struct HuffCode {            // canonical description used for build + long codes
     uint16_t first[16];      // first codeword of each length (MSB-first value)
@@ -136,7 +138,7 @@ struct BitReader {
 // ------------------------------------------------------------ table building
 __device__ __forceinline__ uint32_t make_litlen_entry(unsigned sym, unsigned l)
 {
-    if (sym < 256) return (sym << 16) | K_LIT | l;
+    if (sym < 256) return (sym << 16) | LITFLAG | K_LIT | l;
     if (sym == 256) return K_EOB | l;
     unsigned base, extra;
     length_slot_info(sym - 257, base, extra);
@@ -528,11 +530,72 @@ __device__ __forceinline__ void copy_match_part(const Grp<G> &g, OutState &o, un
 constexpr uint32_t COPY_PART = 4096;
 constexpr uint32_t LONG_D_MAX = 4096;
 constexpr uint32_t LONG_MIN_BODY = 512;
+constexpr uint32_t SMEM_BLOCK_MAX = 1024;        // bytes of BuildScratch + lens usable as a block buffer
 
 // bytes [0, n) of w (n may be <= 0 or >= 4)
 __device__ __forceinline__ uint32_t keep_low_bytes(uint32_t w, int n)
 {
     return n <= 0 ? 0u : n >= 4 ? w : w & ((1u << (8 * n)) - 1u);
+}
+
+// d16[c] = src[c mod nblk] for c < nch, chunk c handled by lane (c mod G).  The loads of four
+// steps are issued before their stores (the compiler cannot know that the stores never hit src).
+template <int G>
+__device__ __forceinline__ void replay_block(const Grp<G> &g, const uint4 *src, uint4 *d16, uint32_t nch, uint32_t nblk)
+{
+    uint32_t j = g.lane % nblk, c = g.lane;
+    const uint32_t gs = (uint32_t)G % nblk;
+#pragma unroll 1
+    for (; c + 3 * G < nch; c += 4 * G) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            v[u] = src[j];
+            j += gs;
+            if (j >= nblk) j -= nblk;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) d16[c + u * G] = v[u];
+    }
+#pragma unroll 1
+    for (; c < nch; c += G) {
+        d16[c] = src[j];
+        j += gs;
+        if (j >= nblk) j -= nblk;
+    }
+}
+
+// Block sums for the closed-form Adler-32 of a replayed block: SD = sum blk[k], WD = sum k*blk[k]
+// over the whole block, SR / WR the same over k < r; reduced over the group, all mod 65521.
+template <int G>
+__device__ __forceinline__ void block_sums(const Grp<G> &g, const uint4 *blk, uint32_t nblk, uint32_t r,
+                                           uint32_t &SD, uint32_t &WD, uint32_t &SR, uint32_t &WR)
+{
+    SD = 0; WD = 0; SR = 0; WR = 0;
+    for (uint32_t k = g.lane; k < nblk; k += G) {
+        const uint4 x = blk[k];
+        const uint32_t sx = __dp4a(x.x, 0x01010101u, __dp4a(x.y, 0x01010101u, __dp4a(x.z, 0x01010101u, __dp4a(x.w, 0x01010101u, 0u))));
+        const uint32_t wx = 16u * k * sx + __dp4a(x.x, 0x03020100u, __dp4a(x.y, 0x07060504u, __dp4a(x.z, 0x0B0A0908u, __dp4a(x.w, 0x0F0E0D0Cu, 0u))));
+        SD += sx;
+        WD += wx;
+        if (k < (r >> 4)) { SR += sx; WR += wx; }
+    }
+    if ((r & 15u) && g.lane == 0) {           // the chunk the remainder ends in
+        const uint32_t k = r >> 4;
+        const int nb = (int)(r & 15u);
+        uint4 x = blk[k];
+        x.x = keep_low_bytes(x.x, nb); x.y = keep_low_bytes(x.y, nb - 4);
+        x.z = keep_low_bytes(x.z, nb - 8); x.w = keep_low_bytes(x.w, nb - 12);
+        const uint32_t sx = __dp4a(x.x, 0x01010101u, __dp4a(x.y, 0x01010101u, __dp4a(x.z, 0x01010101u, __dp4a(x.w, 0x01010101u, 0u))));
+        SR += sx;
+        WR += 16u * k * sx + __dp4a(x.x, 0x03020100u, __dp4a(x.y, 0x07060504u, __dp4a(x.z, 0x0B0A0908u, __dp4a(x.w, 0x0F0E0D0Cu, 0u))));
+    }
+    SD %= 65521u; WD %= 65521u; SR %= 65521u; WR %= 65521u;
+#pragma unroll
+    for (int sft = G / 2; sft > 0; sft >>= 1) {
+        SD += g.shfl_xor(SD, sft); WD += g.shfl_xor(WD, sft);
+        SR += g.shfl_xor(SR, sft); WR += g.shfl_xor(WR, sft);
+    }
 }
 
 template <bool ADLER, int G>
@@ -561,70 +624,33 @@ __device__ __forceinline__ void copy_match(const Grp<G> &g, OutState &o, unsigne
         const uint32_t nch = n2 >> 4, nblk = dist >> 4;
         uint4 *d16 = reinterpret_cast<uint4 *>(o.out + p2);
         const uint4 *blk = reinterpret_cast<const uint4 *>(o.out + p2 - dist);
-        {
-            // loads of four steps first: the compiler cannot know that the stores never hit the block
-            uint32_t j = g.lane % nblk, c = g.lane;
-            const uint32_t gs = (uint32_t)G % nblk;
-#pragma unroll 1
-            for (; c + 3 * G < nch; c += 4 * G) {
-                uint4 v[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    v[u] = blk[j];
-                    j += gs;
-                    if (j >= nblk) j -= nblk;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) d16[c + u * G] = v[u];
-            }
-#pragma unroll 1
-            for (; c < nch; c += G) {
-                d16[c] = blk[j];
-                j += gs;
-                if (j >= nblk) j -= nblk;
-            }
+        const uint32_t q = n2 / dist, r = n2 - q * dist;
+        uint32_t SD = 0, WD = 0, SR = 0, WR = 0;
+        if (dist <= SMEM_BLOCK_MAX) {
+            // small blocks are staged in shared memory (the table builder's scratch is idle while
+            // symbols are decoded): no L1 tags, no misses, ~25 cycles per load
+            uint4 *sb = reinterpret_cast<uint4 *>(ext);
+            for (uint32_t k = g.lane; k < nblk; k += G) sb[k] = blk[k];
+            g.sync();
+            replay_block<G>(g, sb, d16, nch, nblk);
+            if (ADLER) block_sums<G>(g, sb, nblk, r, SD, WD, SR, WR);
+            g.sync();                                 // ext is reused by the next match
+        } else {
+            replay_block<G>(g, blk, d16, nch, nblk);
+            if (ADLER) block_sums<G>(g, blk, nblk, r, SD, WD, SR, WR);
         }
         const uint32_t tail = n2 & 15u;
         if (g.lane < tail)
             o.out[p2 + 16 * nch + g.lane] = reinterpret_cast<const uint8_t *>(blk)[16 * (nch % nblk) + g.lane];
-        if (ADLER) {
-            const uint32_t q = n2 / dist, r = n2 - q * dist;
-            // block sums: SD = sum blk[k], WD = sum k*blk[k]; SR, WR the same over k < r
-            uint32_t SD = 0, WD = 0, SR = 0, WR = 0;
-            for (uint32_t k = g.lane; k < nblk; k += G) {
-                const uint4 x = blk[k];
-                const uint32_t sx = __dp4a(x.x, 0x01010101u, __dp4a(x.y, 0x01010101u, __dp4a(x.z, 0x01010101u, __dp4a(x.w, 0x01010101u, 0u))));
-                const uint32_t wx = 16u * k * sx + __dp4a(x.x, 0x03020100u, __dp4a(x.y, 0x07060504u, __dp4a(x.z, 0x0B0A0908u, __dp4a(x.w, 0x0F0E0D0Cu, 0u))));
-                SD += sx;
-                WD += wx;
-                if (k < (r >> 4)) { SR += sx; WR += wx; }
-            }
-            if ((r & 15u) && g.lane == 0) {           // the chunk the remainder ends in
-                const uint32_t k = r >> 4;
-                const int nb = (int)(r & 15u);
-                uint4 x = blk[k];
-                x.x = keep_low_bytes(x.x, nb); x.y = keep_low_bytes(x.y, nb - 4);
-                x.z = keep_low_bytes(x.z, nb - 8); x.w = keep_low_bytes(x.w, nb - 12);
-                const uint32_t sx = __dp4a(x.x, 0x01010101u, __dp4a(x.y, 0x01010101u, __dp4a(x.z, 0x01010101u, __dp4a(x.w, 0x01010101u, 0u))));
-                SR += sx;
-                WR += 16u * k * sx + __dp4a(x.x, 0x03020100u, __dp4a(x.y, 0x07060504u, __dp4a(x.z, 0x0B0A0908u, __dp4a(x.w, 0x0F0E0D0Cu, 0u))));
-            }
-            SD %= 65521u; WD %= 65521u; SR %= 65521u; WR %= 65521u;
-#pragma unroll
-            for (int sft = G / 2; sft > 0; sft >>= 1) {
-                SD += g.shfl_xor(SD, sft); WD += g.shfl_xor(WD, sft);
-                SR += g.shfl_xor(SR, sft); WR += g.shfl_xor(WR, sft);
-            }
-            if (g.lane == 0) {
-                // sum over m < q, k < D of (p2 + m*D + k) blk[k]  +  sum over k < r of (p2 + q*D + k) blk[k]
-                const uint64_t M = 65521u;
-                const uint64_t sd = SD % M, wd = WD % M, sr = SR % M, wr = WR % M;
-                const uint64_t qm = q % M, pm = p2 % M, dm = dist % M;
-                const uint64_t tri = ((uint64_t)q * (q - (q ? 1u : 0u)) / 2u) % M;
-                uint64_t db = qm * pm % M * sd + dm * sd % M * tri + qm * wd + (pm + qm * dm) % M * sr + wr;
-                o.sumA += (uint32_t)((qm * sd + sr) % M);
-                o.sumB += db % M;
-            }
+        if (ADLER && g.lane == 0) {
+            // sum over m < q, k < D of (p2 + m*D + k) blk[k]  +  sum over k < r of (p2 + q*D + k) blk[k]
+            const uint64_t M = 65521u;
+            const uint64_t sd = SD % M, wd = WD % M, sr = SR % M, wr = WR % M;
+            const uint64_t qm = q % M, pm = p2 % M, dm = dist % M;
+            const uint64_t tri = ((uint64_t)q * (q - (q ? 1u : 0u)) / 2u) % M;
+            const uint64_t db = qm * pm % M * sd + dm * sd % M * tri + qm * wd + (pm + qm * dm) % M * sr + wr;
+            o.sumA += (uint32_t)((qm * sd + sr) % M);
+            o.sumB += db % M;
         }
         o.pos += n2;
     }
@@ -643,32 +669,57 @@ __device__ __forceinline__ void copy_match(const Grp<G> &g, OutState &o, unsigne
 constexpr uint32_t COALESCE_MAX = BDF_COALESCE_MAX;
 constexpr uint32_t COALESCE_MIN_LEN = 64;
 
+// One decoding step of a Huffman block: up to two literals, or one match (with everything that
+// coalesces into it), or the end of the block.  Returns STEP_MORE, or the status that ends the
+// block (BDF_OK at end-of-block).  The callers' loops are WARP-uniform (see inflate_stream): every
+// lane group of the warp enters each step together, which is what keeps groups with similar
+// streams on one instruction stream.
+constexpr int STEP_MORE = -1;
 template <bool ADLER, int G>
-__device__ int decode_huffman_block(const Grp<G> &g, BitReader &br, OutState &o, InflateSmem<G> &sm)
+__device__ __forceinline__ int decode_step(const Grp<G> &g, BitReader &br, OutState &o, InflateSmem<G> &sm)
 {
-    for (;;) {
-        // more than two zero-fill words loaded: the stream ended inside this block
-        if (br.widx > br.nwords + 2) return BDF_SHORT_INPUT;
-        br.refill();
+    // A literal: parked in lane npend of the group, flushed as one store when every lane has one.
+#define BDF_PARK_LITERAL(e)                                                          \
+    do {                                                                             \
+        if (o.pos + o.npend >= o.cap) return BDF_INSUFFICIENT_SPACE;                 \
+        br.drop((e) & 31u);                                                          \
+        if (g.lane == o.npend) o.mylit = (e) >> 16;                                  \
+        if (++o.npend == G) {                                                        \
+            make_valid<G>(g, o, o.pos + 2 * G);                                      \
+            flush_literals<ADLER>(o, g.lane);                                        \
+        }                                                                            \
+    } while (0)
+    {
+        if (br.left <= 32) {
+            // more than two zero-fill words loaded: the stream ended inside this block
+            if (br.widx > br.nwords + 2) return BDF_SHORT_INPUT;
+            br.refill();
+        }
+        uint32_t e = sm.lit_tab[br.peek(LT_BITS)];
+        if (e & LITFLAG) {
+            // literals come in runs: a second one is looked up without another refill
+            // (a direct literal is at most LT_BITS bits, so >= 24 valid bits remain)
+            BDF_PARK_LITERAL(e);
+            e = sm.lit_tab[br.peek(LT_BITS)];
+            if (e & LITFLAG) {
+                BDF_PARK_LITERAL(e);
+                return STEP_MORE;
+            }
+            br.refill();                               // the general path starts from >= 33 valid bits
+        }
         const uint32_t tok_lo = (uint32_t)br.buf;      // >= 33 valid bits: the next 32 bits of the stream
         const int32_t tok_left = br.left;
         const uint32_t tok_widx = br.widx;
-        uint32_t e = sm.lit_tab[br.peek(LT_BITS)];
         if ((e & 31u) == 0) {
             e = decode_long<CODE_LITLEN, LT_BITS>(br.peek(15), sm.lit_sorted, sm.lit_code);
             if (e == 0) return BDF_BAD_DATA;
         }
-        br.drop(e & 31u);
         const uint32_t kind = e & K_MASK;
-        if (kind == K_LIT) {
-            if (o.pos + o.npend >= o.cap) return BDF_INSUFFICIENT_SPACE;
-            if (g.lane == o.npend) o.mylit = e >> 16;
-            if (++o.npend == G) {
-                make_valid<G>(g, o, o.pos + 2 * G);
-                flush_literals<ADLER>(o, g.lane);
-            }
-            continue;
+        if (kind == K_LIT) {                           // a literal with a codeword longer than the table
+            BDF_PARK_LITERAL(e);
+            return STEP_MORE;
         }
+        br.drop(e & 31u);
         if (kind == K_EOB) {
             return br.overrun() ? BDF_SHORT_INPUT : BDF_OK;
         }
@@ -743,9 +794,11 @@ __device__ int decode_huffman_block(const Grp<G> &g, BitReader &br, OutState &o,
                 length += len2;
             }
         }
-        copy_match<ADLER, G>(g, o, length, offset, reinterpret_cast<uint8_t *>(sm.bs.cnt));
+        copy_match<ADLER, G>(g, o, length, offset, reinterpret_cast<uint8_t *>(&sm.bs));
         if (ADLER) adler_fold(o);
     }
+    return STEP_MORE;
+#undef BDF_PARK_LITERAL
 }
 
 // read_dynamic_huffman_header, src/decompress/mod.rs:403-507
@@ -785,16 +838,23 @@ __device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, InflateSmem<G
     const unsigned total = nlit + noff;
     unsigned i = 0, prev = 0;
     while (i < total) {
+        // >= 33 valid bits after a refill: up to three plain lengths (<= 7 bits each), or two and
+        // one repeat symbol (<= 7 + 7 bits), are decoded per refill
         br.refill();
-        const uint32_t e = pre_tab[br.peek(PT_BITS)];
+        uint32_t e = pre_tab[br.peek(PT_BITS)];
+        unsigned k = 0;
+        bool again = false;
+        while ((e >> 16) < 16) {
+            if (g.lane == 0) sm.lens[i] = (uint8_t)(e >> 16);
+            prev = e >> 16;
+            br.drop(e & 31u);
+            i++;
+            if (++k == 3 || i >= total) { again = true; break; }
+            e = pre_tab[br.peek(PT_BITS)];
+        }
+        if (again) continue;
         br.drop(e & 31u);
         const unsigned sym = e >> 16;
-        if (sym < 16) {
-            if (g.lane == 0) sm.lens[i] = (uint8_t)sym;
-            prev = sym;
-            i++;
-            continue;
-        }
         unsigned rep, val;
         if (sym == 16) {
             if (i == 0) return BDF_BAD_DATA;
@@ -808,7 +868,7 @@ __device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, InflateSmem<G
             val = 0;
         }
         if (rep > total - i) rep = total - i;      // overruns are clamped (:462-493)
-        for (unsigned k = g.lane; k < rep; k += G) sm.lens[i + k] = (uint8_t)val;
+        for (unsigned q = g.lane; q < rep; q += G) sm.lens[i + q] = (uint8_t)val;
         prev = val;
         i += rep;
     }
@@ -832,54 +892,81 @@ __device__ void load_static_codes(const Grp<G> &g, InflateSmem<G> &sm)
 }
 
 // Raw DEFLATE stream [p, p+len) -> o; returns status, *used = bytes consumed.
+// Called by ALL lanes of the warp together; `have` says whether this group has a stream.  Both
+// loops run until no group of the warp has work left (a group that is done idles), so the groups
+// meet again at every block header and at every decoding step.
 template <bool ADLER, int G>
 __device__ int inflate_stream(const Grp<G> &g, const uint8_t *p, uint32_t len, OutState &o, InflateSmem<G> &sm,
-                              uint32_t *used)
+                              uint32_t *used, bool have)
 {
     BitReader br;
-    br.init(p, len);
-    int st;
-    for (;;) {
-        br.refill();
-        if (br.consumed_bits() + 3 > (int64_t)len * 8) { st = BDF_SHORT_INPUT; break; }
-        const unsigned final = br.take(1);
-        const unsigned type = br.take(2);
-        if (type == 0) {
-            // stored block (src/decompress/mod.rs:282-346, x86.rs:2216-2246)
-            uint32_t at = (uint32_t)((br.consumed_bits() + 7) >> 3);
-            if (at + 4 > len) { st = BDF_SHORT_INPUT; break; }
-            const unsigned blen = p[at] | (unsigned)p[at + 1] << 8;
-            const unsigned nlen = p[at + 2] | (unsigned)p[at + 3] << 8;
-            at += 4;
-            if (blen != (~nlen & 0xFFFFu)) { st = BDF_BAD_DATA; break; }
-            if (o.pos + blen > o.cap) { st = BDF_INSUFFICIENT_SPACE; break; }
-            if (at + blen > len) { st = BDF_SHORT_INPUT; break; }
-            for (unsigned i = g.lane; i < blen; i += G) {
-                const uint8_t b = p[at + i];
-                o.out[o.pos + i] = b;
-                adler_acc1<ADLER>(o, o.pos + i, b);
-            }
-            o.pos += blen;
-            if (ADLER) adler_fold(o);
-            br.seek(at + blen);
-        } else if (type == 3) {
-            st = BDF_BAD_DATA;
-            break;
-        } else {
-            if (type == 1) {
-                load_static_codes<G>(g, sm);
-            } else {
-                st = read_dynamic_header<G>(g, br, sm);
-                if (st != BDF_OK) break;
-            }
-            g.sync();
-            st = decode_huffman_block<ADLER, G>(g, br, o, sm);
-            flush_literals<ADLER>(o, g.lane);
-            if (st != BDF_OK) break;
+    br.p = p; br.len = 0; br.mis = 0; br.nwords = 0; br.widx = 0; br.ahead = 0; br.buf = 0; br.left = 0;
+    if (have) br.init(p, len);
+    int st = BDF_OK;
+    bool live = have;
+    while (__any_sync(BDF_FULL_MASK, live)) {
+        bool inblock = false;
+        unsigned final = 0;
+        if (live) {
+            br.refill();
+            if (br.consumed_bits() + 3 > (int64_t)len * 8) { st = BDF_SHORT_INPUT; live = false; }
         }
-        if (final) { st = BDF_OK; break; }
+        if (live) {
+            final = br.take(1);
+            const unsigned type = br.take(2);
+            if (type == 0) {
+                // stored block (src/decompress/mod.rs:282-346, x86.rs:2216-2246)
+                uint32_t at = (uint32_t)((br.consumed_bits() + 7) >> 3);
+                unsigned blen = 0;
+                if (at + 4 > len) st = BDF_SHORT_INPUT;
+                else {
+                    blen = p[at] | (unsigned)p[at + 1] << 8;
+                    const unsigned nlen = p[at + 2] | (unsigned)p[at + 3] << 8;
+                    at += 4;
+                    if (blen != (~nlen & 0xFFFFu)) st = BDF_BAD_DATA;
+                    else if (o.pos + blen > o.cap) st = BDF_INSUFFICIENT_SPACE;
+                    else if (at + blen > len) st = BDF_SHORT_INPUT;
+                }
+                if (st == BDF_OK) {
+                    for (unsigned i = g.lane; i < blen; i += G) {
+                        const uint8_t b = p[at + i];
+                        o.out[o.pos + i] = b;
+                        adler_acc1<ADLER>(o, o.pos + i, b);
+                    }
+                    o.pos += blen;
+                    if (ADLER) adler_fold(o);
+                    br.seek(at + blen);
+                    if (final) live = false;
+                } else {
+                    live = false;
+                }
+            } else if (type == 3) {
+                st = BDF_BAD_DATA;
+                live = false;
+            } else {
+                if (type == 1) {
+                    load_static_codes<G>(g, sm);
+                } else {
+                    st = read_dynamic_header<G>(g, br, sm);
+                    if (st != BDF_OK) live = false;
+                }
+                g.sync();
+                inblock = live;
+            }
+        }
+        while (__any_sync(BDF_FULL_MASK, inblock)) {
+            if (inblock) {
+                const int r = decode_step<ADLER, G>(g, br, o, sm);
+                if (r != STEP_MORE) {
+                    inblock = false;
+                    flush_literals<ADLER>(o, g.lane);
+                    if (r != BDF_OK) { st = r; live = false; }
+                    else if (final) live = false;
+                }
+            }
+        }
     }
-    int64_t cb = br.consumed_bits();
+    int64_t cb = have ? br.consumed_bits() : 0;
     if (cb < 0) cb = 0;
     *used = (uint32_t)((cb + 7) >> 3);
     g.sync();
@@ -962,6 +1049,9 @@ inflate_kernel(InflateArgs a)
     __shared__ uint32_t s_crc[FORMAT == BDF_GZIP ? 4 : 1][256];
     __shared__ uint32_t s_x2n[32];
     InflateSmem<G> &sm = reinterpret_cast<InflateSmem<G> *>(smem_raw)[threadIdx.x / G];
+    static_assert(offsetof(InflateSmem<G>, bs) % 16 == 0 && sizeof(InflateSmem<G>) % 16 == 0 &&
+                      offsetof(InflateSmem<G>, lens) + sizeof(sm.lens) - offsetof(InflateSmem<G>, bs) >= SMEM_BLOCK_MAX,
+                  "builder scratch + lens double as the 16-byte aligned block buffer of copy_match");
     const Grp<G> g;
     if (FORMAT == BDF_GZIP) {
         for (unsigned i = threadIdx.x; i < 1024; i += blockDim.x) s_crc[i >> 8][i & 255] = g_crc_tables.slice[i >> 8][i & 255];
@@ -978,12 +1068,17 @@ inflate_kernel(InflateArgs a)
         idx = __shfl_sync(BDF_FULL_MASK, idx, 0);
         if (idx >= a.n) break;
         idx += lane_id() / G;
-        if (idx < a.n) {
-        const uint8_t *p = a.in + a.in_off[idx];
-        const uint64_t len64 = a.in_off[idx + 1] - a.in_off[idx];
-        const uint64_t cap64 = a.max_out[idx];
+        const bool have = idx < a.n;
+        const uint8_t *p = a.in;
+        uint64_t len64 = 0, cap64 = 0;
         OutState o;
-        o.out = a.out + a.out_off[idx];
+        o.out = a.out;
+        if (have) {
+            p = a.in + a.in_off[idx];
+            len64 = a.in_off[idx + 1] - a.in_off[idx];
+            cap64 = a.max_out[idx];
+            o.out = a.out + a.out_off[idx];
+        }
         o.pos = 0;
         o.cap = cap64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)cap64;
         o.npend = 0; o.mylit = 0; o.sumA = 0; o.sumB = 0; o.next_fold = ADLER_FOLD_INTERVAL;
@@ -995,63 +1090,67 @@ inflate_kernel(InflateArgs a)
             o.zfill = first;
             o.zlimit = last > (int64_t)first ? (uint32_t)last : first;
         }
+        // framing in front of the DEFLATE data: decides whether (and where) this group inflates
         int st = BDF_OK;
-        uint32_t sum = 0, used = 0;
-        if (len64 > 0xFFFFFFF0ull) {
+        uint32_t sum = 0, used = 0, at = 0, dlen = 0;
+        const uint32_t len = (uint32_t)len64;
+        if (!have) {
+            st = BDF_BAD_DATA;
+        } else if (len64 > 0xFFFFFFF0ull) {
             st = BDF_BAD_DATA;      // single streams above 4 GiB are outside this engine's range
         } else if (FORMAT == BDF_RAW) {
-            st = inflate_stream<false, G>(g, p, (uint32_t)len64, o, sm, &used);
+            dlen = len;
         } else if (FORMAT == BDF_ZLIB) {
             // decompress_zlib_uninit, src/decompress/mod.rs:1074-1127
-            const uint32_t len = (uint32_t)len64;
             if (len < 6) st = BDF_SHORT_INPUT;
             else {
                 const unsigned hdr = (unsigned)p[0] << 8 | p[1];
                 if (hdr % 31 != 0 || ((hdr >> 8) & 0xF) != 8 || ((hdr >> 12) & 0xF) > 7 || ((hdr >> 5) & 1))
                     st = BDF_BAD_DATA;
-                else {
-                    st = inflate_stream<true, G>(g, p + 2, len - 6, o, sm, &used);
-                    if (st == BDF_OK) {
-                        sum = grp_adler_finish<G>(g, o.sumA, o.sumB, o.pos);
-                        const uint8_t *f = p + 2 + used;
-                        const uint32_t want = (uint32_t)f[0] << 24 | (uint32_t)f[1] << 16 | (uint32_t)f[2] << 8 | f[3];
-                        if (want != sum) st = BDF_BAD_DATA;
-                    }
-                }
+                at = 2;
+                dlen = len - 6;
             }
         } else {
             // decompress_gzip_uninit, src/decompress/mod.rs:1144-1240
-            const uint32_t len = (uint32_t)len64;
             if (len < 18) st = BDF_SHORT_INPUT;
             else if (p[0] != 0x1F || p[1] != 0x8B || p[2] != 8 || (p[3] & 0xE0)) st = BDF_BAD_DATA;
             else {
                 const unsigned flg = p[3];
-                uint64_t at = 10;
+                uint64_t h = 10;
                 if (flg & 0x04) {
-                    if (at + 2 > len) st = BDF_SHORT_INPUT;
-                    else at += 2 + (p[at] | (uint64_t)p[at + 1] << 8);
+                    if (h + 2 > len) st = BDF_SHORT_INPUT;
+                    else h += 2 + (p[h] | (uint64_t)p[h + 1] << 8);
                 }
-                if (st == BDF_OK && (flg & 0x08)) { while (at < len && p[at]) at++; at++; }
-                if (st == BDF_OK && (flg & 0x10)) { while (at < len && p[at]) at++; at++; }
-                if (st == BDF_OK && (flg & 0x02)) at += 2;
-                if (st == BDF_OK && at + 8 > len) st = BDF_SHORT_INPUT;
-                if (st == BDF_OK) {
-                    st = inflate_stream<false, G>(g, p + at, (uint32_t)(len - 8 - at), o, sm, &used);
-                    if (st == BDF_OK) {
-                        sum = grp_crc32<G>(g, o.out, o.pos, s_crc, s_x2n);
-                        const uint8_t *f = p + at + used;
-                        const uint32_t want = (uint32_t)f[3] << 24 | (uint32_t)f[2] << 16 | (uint32_t)f[1] << 8 | f[0];
-                        const uint32_t isz = (uint32_t)f[7] << 24 | (uint32_t)f[6] << 16 | (uint32_t)f[5] << 8 | f[4];
-                        if (want != sum || isz != o.pos) st = BDF_BAD_DATA;
-                    }
-                }
+                if (st == BDF_OK && (flg & 0x08)) { while (h < len && p[h]) h++; h++; }
+                if (st == BDF_OK && (flg & 0x10)) { while (h < len && p[h]) h++; h++; }
+                if (st == BDF_OK && (flg & 0x02)) h += 2;
+                if (st == BDF_OK && h + 8 > len) st = BDF_SHORT_INPUT;
+                if (st == BDF_OK) { at = (uint32_t)h; dlen = (uint32_t)(len - 8 - h); }
             }
         }
-        if (g.lane == 0) {
+        const bool go = st == BDF_OK;
+        // all lanes of the warp call this together (see inflate_stream)
+        const int ist = inflate_stream<FORMAT == BDF_ZLIB, G>(g, p + at, dlen, o, sm, &used, go);
+        if (go) {
+            st = ist;
+            if (st == BDF_OK && FORMAT == BDF_ZLIB) {
+                sum = grp_adler_finish<G>(g, o.sumA, o.sumB, o.pos);
+                const uint8_t *f = p + at + used;
+                const uint32_t want = (uint32_t)f[0] << 24 | (uint32_t)f[1] << 16 | (uint32_t)f[2] << 8 | f[3];
+                if (want != sum) st = BDF_BAD_DATA;
+            }
+            if (st == BDF_OK && FORMAT == BDF_GZIP) {
+                sum = grp_crc32<G>(g, o.out, o.pos, s_crc, s_x2n);
+                const uint8_t *f = p + at + used;
+                const uint32_t want = (uint32_t)f[3] << 24 | (uint32_t)f[2] << 16 | (uint32_t)f[1] << 8 | f[0];
+                const uint32_t isz = (uint32_t)f[7] << 24 | (uint32_t)f[6] << 16 | (uint32_t)f[5] << 8 | f[4];
+                if (want != sum || isz != o.pos) st = BDF_BAD_DATA;
+            }
+        }
+        if (have && g.lane == 0) {
             a.status[idx] = st;
             a.out_size[idx] = st == BDF_OK ? o.pos : 0;
             if (a.checksum) a.checksum[idx] = st == BDF_OK ? sum : 0;
-        }
         }
         __syncwarp();
     }
