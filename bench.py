@@ -155,6 +155,70 @@ def cpu_baseline(n_sample, min_seconds, plain, flat, in_off):
                       f"(Rust toolchain unavailable), one codec state per thread"}
 
 
+def pipeline_section(ctx, lib, bdf, dev, stream, n, level, world, barrier, steps=2):
+    """BASELINE configs[4] per-GPU shard: corpus B (mixed text / binary / periodic / low-entropy
+    64 KiB streams) through compress (gzip framing) -> pack -> decompress -> CRC-32 check, all
+    resident in HBM.  16 GiB over 8 GPUs = 2 GiB = 32768 streams per GPU.  Returns per-rank times."""
+    import torch
+    import corpus
+    base = [corpus.corpus_b_stream(k) for k in range(64)]
+    crc = np.array([zlib.crc32(b) for b in base], dtype=np.uint32)
+    tile = np.frombuffer(b"".join(base), dtype=np.uint8)
+    d_plain = torch.from_numpy(np.tile(tile, n // 64)).to(dev)
+    d_in_off = torch.arange(n + 1, dtype=torch.int64, device=dev) * STREAM
+    bound = int(lib.bdf_compress_bound(bdf.GZIP, STREAM))
+    d_slab = torch.empty(n * bound, dtype=torch.uint8, device=dev)
+    d_slab_off = torch.arange(n, dtype=torch.int64, device=dev) * bound
+    d_csize = torch.zeros(n, dtype=torch.int64, device=dev)
+    d_cstat = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    d_dense = torch.empty(n * STREAM, dtype=torch.uint8, device=dev)     # compressed never exceeds the input here
+    d_dense_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    d_out = torch.empty(n * STREAM, dtype=torch.uint8, device=dev)
+    d_out_off = torch.arange(n, dtype=torch.int64, device=dev) * STREAM
+    d_max = torch.full((n,), STREAM, dtype=torch.int64, device=dev)
+    d_osize = torch.zeros(n, dtype=torch.int64, device=dev)
+    d_ostat = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    d_sum = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_exp = torch.from_numpy(np.tile(crc, n // 64).view(np.int32)).to(dev)
+    sp = C.c_void_p(stream.cuda_stream)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def one(record):
+        if record:
+            ev[0].record(stream)
+        ctx.check(lib.bdf_compress_batch_device(ctx.handle, level, bdf.GZIP, d_plain.data_ptr(), d_in_off.data_ptr(),
+                                                n, d_slab.data_ptr(), d_slab_off.data_ptr(), d_csize.data_ptr(),
+                                                d_cstat.data_ptr(), sp))
+        if record:
+            ev[1].record(stream)
+        torch.cumsum(d_csize, 0, out=d_dense_off[1:])
+        ctx.check(lib.bdf_gather_streams_device(ctx.handle, d_slab.data_ptr(), d_slab_off.data_ptr(),
+                                                d_csize.data_ptr(), n, d_dense.data_ptr(), d_dense_off.data_ptr(), sp))
+        if record:
+            ev[2].record(stream)
+        ctx.check(lib.bdf_decompress_batch_device(ctx.handle, bdf.GZIP, d_dense.data_ptr(), d_dense_off.data_ptr(), n,
+                                                  d_out.data_ptr(), d_out_off.data_ptr(), d_max.data_ptr(),
+                                                  d_osize.data_ptr(), d_sum.data_ptr(), d_ostat.data_ptr(), sp))
+        ok = (d_sum == d_exp).all() & (d_ostat == 0).all() & (d_cstat == 0).all()
+        if record:
+            ev[3].record(stream)
+        return ok
+
+    assert bool(one(False).item()), "pipeline parity (CRC-32 of the round trip) failed"
+    assert d_out[(n - 1) * STREAM:].cpu().numpy().tobytes() == base[(n - 1) % 64]
+    barrier()
+    t_c = t_p = t_d = 0.0
+    for _ in range(steps):
+        ok = one(True)
+        torch.cuda.synchronize(dev)
+        assert bool(ok.item())
+        t_c += ev[0].elapsed_time(ev[1]); t_p += ev[1].elapsed_time(ev[2]); t_d += ev[2].elapsed_time(ev[3])
+    barrier()
+    comp_bytes = int(d_csize.sum().item())
+    return {"t_compress_ms": t_c / steps, "t_pack_ms": t_p / steps, "t_decompress_ms": t_d / steps,
+            "bytes": n * STREAM, "comp_bytes": comp_bytes}
+
+
 def run_reference(args):
     """Reference arm: the CPU restatement on the host cores, same metric / config."""
     rank = int(os.environ.get("RANK", "0"))
@@ -198,6 +262,9 @@ def main():
     ap.add_argument("--streams", type=int, default=N_STREAMS, help="streams per GPU (default: the BASELINE config)")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline-streams", type=int, default=32768,
+                    help="streams per GPU of the mixed-corpus compress+decompress+CRC pipeline (0 = skip)")
+    ap.add_argument("--pipeline-level", type=int, default=6)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -324,6 +391,31 @@ def main():
     h2d = comp_bytes + (n + 1) * 8 + 2 * n * 8
     d2h = out_bytes + n * 8 + n * 4 + n * 4
 
+    # ---- configs[4]: mixed corpus, compress -> decompress -> CRC-32, sharded by stream (extra section)
+    pipe = None
+    if args.pipeline_streams >= 64:
+        lib.bdf_host_free(h_out_p)
+        h_out_p = None
+        torch.cuda.empty_cache()
+        launches_p0 = ctx.kernel_launches
+        pr = pipeline_section(ctx, lib, bdf, dev, stream, args.pipeline_streams // 64 * 64, args.pipeline_level,
+                              world, barrier)
+        tt = torch.tensor([pr["t_compress_ms"], pr["t_pack_ms"], pr["t_decompress_ms"],
+                           pr["t_compress_ms"] + pr["t_pack_ms"] + pr["t_decompress_ms"]],
+                          dtype=torch.float64, device=dev)
+        cb = torch.tensor([pr["comp_bytes"]], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cb, op=dist.ReduceOp.SUM)
+        tc, tp, td, tall = [float(x) for x in tt.tolist()]
+        ub = world * pr["bytes"]
+        pipe = {"workload": f"corpus B (mixed text/binary/periodic/low-entropy), {pr['bytes'] >> 20} MiB per GPU, "
+                            f"level {args.pipeline_level} gzip: compress -> pack -> decompress, CRC-32 of every "
+                            f"stream checked against the input's", "unit": "GB/s (uncompressed)",
+                "pipeline": ub / (tall * 1e-3) / 1e9, "compress": ub / (tc * 1e-3) / 1e9,
+                "decompress": ub / (td * 1e-3) / 1e9, "pack_ms": tp, "ratio": ub / int(cb.item()),
+                "kernel_launches_per_step": int((ctx.kernel_launches - launches_p0) // 3)}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         kernel_ms = float(np.mean(step_ms))
@@ -351,13 +443,16 @@ def main():
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms},
             "clocks": clocks.summary(),
         }
+        if pipe:
+            line["mixed_pipeline"] = pipe
         if world == 1 and not args.no_cpu_baseline:
             import oracle_lib as o
             o.build()
             line["cpu_baseline"] = cpu_baseline(min(n, 4096), 5.0, plain, flat, in_off)
         print(json.dumps(line), flush=True)
     lib.bdf_host_free(h_in_p)
-    lib.bdf_host_free(h_out_p)
+    if h_out_p:
+        lib.bdf_host_free(h_out_p)
     if world > 1:
         dist.destroy_process_group()
 

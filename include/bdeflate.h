@@ -139,6 +139,18 @@ int bdf_checksum_batch_device(bdf_ctx *ctx, int kind, const uint8_t *in,
 int bdf_checksum_batch_host(bdf_ctx *ctx, int kind, const uint8_t *in,
                             const uint64_t *in_off, size_t n, uint32_t *out);
 
+/*
+ * Packs a bound-spaced result slab (stream i at src + src_off[i], size[i] bytes) into a dense
+ * flat buffer: stream i goes to dst + dst_off[i], dst_off[n+1] being the exclusive prefix sums
+ * of size[] (the caller computes them).  This is the device-side form of the slicing the
+ * reference does on the host after its GPU call (src/batch_cuda.rs:123-137) and of the per-result
+ * copy in src/batch.rs:51; it turns the output of bdf_compress_batch_device into the input layout
+ * of bdf_decompress_batch_device without leaving the GPU.
+ */
+int bdf_gather_streams_device(bdf_ctx *ctx, const uint8_t *src, const uint64_t *src_off,
+                              const uint64_t *size, size_t n, uint8_t *dst,
+                              const uint64_t *dst_off, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ EXPORTS = [
     "bdf_kernel_launches", "bdf_last_kernel_ms", "bdf_host_alloc", "bdf_host_free",
     "bdf_compress_bound", "bdf_decompress_batch_device", "bdf_decompress_batch_host",
     "bdf_compress_batch_device", "bdf_compress_batch_host", "bdf_checksum_batch_device",
-    "bdf_checksum_batch_host",
+    "bdf_checksum_batch_host", "bdf_gather_streams_device",
 ]
 
 
@@ -64,6 +64,8 @@ def load():
     L.bdf_checksum_batch_device.argtypes = [vp, C.c_int, vp, vp, sz, vp, vp]
     L.bdf_checksum_batch_host.restype = C.c_int
     L.bdf_checksum_batch_host.argtypes = [vp, C.c_int, vp, vp, sz, vp]
+    L.bdf_gather_streams_device.restype = C.c_int
+    L.bdf_gather_streams_device.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
     return L
 
 

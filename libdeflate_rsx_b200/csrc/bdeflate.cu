@@ -16,6 +16,7 @@
 #include "checksum.cuh"
 #include "inflate.cuh"
 #include "deflate.cuh"
+#include "gather.cuh"
 
 namespace {
 
@@ -418,6 +419,26 @@ int bdf_checksum_batch_host(bdf_ctx *ctx, int kind, const uint8_t *in, const uin
     CK(cudaMemcpyAsync(out, ctx->checksum.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    return BDF_E_OK;
+}
+
+// ------------------------------------------------------------------ gather
+int bdf_gather_streams_device(bdf_ctx *ctx, const uint8_t *src, const uint64_t *src_off, const uint64_t *size,
+                              size_t n, uint8_t *dst, const uint64_t *dst_off, void *stream)
+{
+    if (!ctx) return BDF_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (n == 0) return BDF_E_OK;
+    if (!src || !src_off || !size || !dst || !dst_off) return fail(ctx, BDF_E_ARG, "null pointer");
+    if (n > 0xFFFFFFF0ull) return fail(ctx, BDF_E_ARG, "too many streams");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    bdf::GatherArgs a{src, src_off, size, dst, dst_off, (uint32_t)n};
+    unsigned long long want = (n + bdf::GATHER_WARPS - 1) / bdf::GATHER_WARPS;
+    unsigned long long full = (unsigned long long)ctx->sm_count * 16;
+    bdf::gather_kernel<<<(unsigned)(want < full ? want : full), bdf::GATHER_WARPS * 32, 0, s>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
     return BDF_E_OK;
 }
 
