@@ -438,8 +438,11 @@ def main():
                     "steps": e2e_steps, "api": "bdf_decompress_batch_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                         "frac": achieved / peak,
+                         "traffic": (traffic["dram_bytes_per_stream"] * n if traffic else None),
                          "kernel": "bdf::inflate_kernel<BDF_ZLIB>", "peak_source": peak_src,
+                         "traffic_source": (f"ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch over "
+                                            f"{traffic['streams_in_capture']} streams ({traffic['report']}), scaled per stream to this launch" if traffic else None),
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms},
             "clocks": clocks.summary(),
         }

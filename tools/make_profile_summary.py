@@ -46,14 +46,25 @@ lines = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.p
 out += ["", "## Warp instructions and stall samples by source line (top 25)", "", "```", lines.rstrip(), "```"]
 if launches and os.path.exists(launches):
     ls = [r for r in csv.reader(open(launches)) if len(r) > 14 and r[0].isdigit()]
-    out += ["", f"## Launch list (`{os.path.basename(launches)}`, `--metrics gpu__time_duration.sum`)", "",
-            "| # | kernel | grid | block | ns |", "|---|---|---|---|---|"]
+    out += ["", f"## Launch list (`{os.path.basename(launches)}`, `--metrics gpu__time_duration.sum`), by kernel", "",
+            "The command is the default `bench.py` run: warm-up + timed steps of the headline (one",
+            "`inflate_kernel<1, 16>` launch per step, nothing else inside the timed region), the end-to-end arm,",
+            "then the mixed-corpus pipeline section (deflate_hc / gather / inflate_kernel<2, 16>).  torch's own",
+            "`at::` kernels are the parity checks between the sections.", "",
+            "| kernel | launches | total ns | mean ns | share of all listed |", "|---|---|---|---|---|"]
     tot = sum(float(r[14].replace(",", "")) for r in ls) or 1
+    agg = {}
     for r in ls:
-        out.append(f"| {r[0]} | `{r[4][:70]}` | {r[8]} | {r[7]} | {r[14]} |")
-    share = sum(float(r[14].replace(",", "")) for r in ls if "inflate_kernel" in r[4]) / tot
+        name = r[4].split("(")[0][:60]
+        a_ = agg.setdefault(name, [0, 0.0, r[8], r[7]])
+        a_[0] += 1
+        a_[1] += float(r[14].replace(",", ""))
+    for name, (cnt, ns, grid, block) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        out.append(f"| `{name}` | {cnt} | {ns:.0f} | {ns / cnt:.0f} | {100 * ns / tot:.1f} % |")
+    ours = sum(v[1] for k, v in agg.items() if "bdf::" in k)
     out.append("")
-    out.append(f"inflate_kernel share of listed GPU time: {100*share:.1f} %")
+    out.append(f"Share of this repo's kernels (`bdf::*`) in the listed GPU time: {100 * ours / tot:.1f} %.  "
+               f"Headline step = one `inflate_kernel<1, 16>` launch = 100 % of its timed region.")
 open(os.path.join(ROOT, "profiles", f"{tag}_summary.md"), "w").write("\n".join(out) + "\n")
 json.dump({"kernel": kernel, "streams_in_capture": nstreams, "dram_bytes_read": rd, "dram_bytes_write": wr,
            "dram_bytes_per_launch": rd + wr, "dram_bytes_per_stream": (rd + wr) / nstreams,
