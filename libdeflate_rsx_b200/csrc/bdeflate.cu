@@ -11,12 +11,12 @@
 #include <string.h>
 #include <mutex>
 #include <new>
+#include <vector>
 
 #include "../../include/bdeflate.h"
 #include "checksum.cuh"
 #include "inflate.cuh"
 #include "deflate.cuh"
-#include "gather.cuh"
 
 namespace {
 
@@ -42,6 +42,7 @@ struct bdf_ctx {
     int inflate_group = 16;                     // lanes per stream in inflate_kernel (BDF_INFLATE_GROUP)
     bdf::DeflateScratch deflate_scratch;
     DevBuf in, out, in_off, out_off, max_out, out_size, status, checksum;
+    DevBuf u_in_off, u_tmp_off, u_size, u_status, u_flags, u_begin, u_tmp;     // chunked compression (units)
 };
 
 namespace {
@@ -170,7 +171,8 @@ void bdf_ctx_destroy(bdf_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->in, &ctx->out, &ctx->in_off, &ctx->out_off, &ctx->max_out,
-                      &ctx->out_size, &ctx->status, &ctx->checksum};
+                      &ctx->out_size, &ctx->status, &ctx->checksum, &ctx->u_in_off, &ctx->u_tmp_off,
+                      &ctx->u_size, &ctx->u_status, &ctx->u_flags, &ctx->u_begin, &ctx->u_tmp};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     bdf::deflate_scratch_free(ctx->deflate_scratch);
@@ -295,7 +297,7 @@ int bdf_compress_batch_device(bdf_ctx *ctx, int level, int format, const uint8_t
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     bdf::DeflateArgs a;
     a.in = in; a.in_off = in_off; a.out = out; a.out_off = out_off; a.out_size = out_size; a.status = status;
-    a.n = (uint32_t)n; a.level = level > 12 ? 12 : level; a.format = format;
+    a.n = (uint32_t)n; a.level = level > 12 ? 12 : level; a.format = format; a.unit_flags = nullptr;
     a.work_counter = next_counter(ctx, s);
     int nl = 0;
     const char *why = nullptr;
@@ -306,19 +308,91 @@ int bdf_compress_batch_device(bdf_ctx *ctx, int level, int format, const uint8_t
     return BDF_E_OK;
 }
 
+// Streams above 64 KiB: units of at most 256 KiB (Compressor::compress, src/compress/mod.rs:699-772)
+// through the 256 KiB kernel instances into a temporary slab, then deflate_join_kernel.  Called with
+// the inputs already on the device and the ctx mutex held.
+static int compress_chunked_locked(bdf_ctx *ctx, int level, int format, const uint64_t *in_off, size_t n,
+                                   cudaStream_t s)
+{
+    constexpr uint64_t CHUNK = 256 * 1024;
+    std::vector<uint64_t> uoff, toff;
+    std::vector<uint8_t> uflags;
+    std::vector<uint32_t> ubegin(n + 1);
+    uint64_t tmp_bytes = 0, max_unit = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t beg = in_off[i], len = in_off[i + 1] - in_off[i];
+        ubegin[i] = (uint32_t)uoff.size();
+        uint64_t ip = 0;
+        do {
+            const uint64_t ul = len - ip < CHUNK ? len - ip : CHUNK;
+            const bool last = ip + ul >= len;
+            uoff.push_back(beg + ip);
+            uflags.push_back(last ? bdf::UNIT_FINISH : bdf::UNIT_SYNC);
+            toff.push_back(tmp_bytes);
+            tmp_bytes += (bdf::deflate_bound(ul) + 15) & ~15ull;
+            if (ul > max_unit) max_unit = ul;
+            ip += ul;
+        } while (ip < len);
+    }
+    const size_t nu = uflags.size();
+    if (nu > 0xFFFFFFF0ull) return fail(ctx, BDF_E_ARG, "too many chunks");
+    ubegin[n] = (uint32_t)nu;
+    uoff.push_back(in_off[n]);
+    int rc;
+    if ((rc = ensure(ctx, ctx->u_in_off, (nu + 1) * 8)) || (rc = ensure(ctx, ctx->u_tmp_off, nu * 8)) ||
+        (rc = ensure(ctx, ctx->u_size, nu * 8)) || (rc = ensure(ctx, ctx->u_status, nu * 4)) ||
+        (rc = ensure(ctx, ctx->u_flags, nu)) || (rc = ensure(ctx, ctx->u_begin, (n + 1) * 4)) ||
+        (rc = ensure(ctx, ctx->u_tmp, tmp_bytes + 16)))
+        return rc;
+    CK(cudaMemcpyAsync(ctx->u_in_off.p, uoff.data(), (nu + 1) * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->u_tmp_off.p, toff.data(), nu * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->u_flags.p, uflags.data(), nu, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->u_begin.p, ubegin.data(), (n + 1) * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));              // the vectors above die with this frame
+    CK(cudaEventRecord(ctx->ev0, s));
+    bdf::DeflateArgs a;
+    a.in = (const uint8_t *)ctx->in.p; a.in_off = (const uint64_t *)ctx->u_in_off.p;
+    a.out = (uint8_t *)ctx->u_tmp.p; a.out_off = (const uint64_t *)ctx->u_tmp_off.p;
+    a.out_size = (uint64_t *)ctx->u_size.p; a.status = (int32_t *)ctx->u_status.p;
+    a.n = (uint32_t)nu; a.level = level > 12 ? 12 : level; a.format = BDF_RAW;
+    a.unit_flags = (const uint8_t *)ctx->u_flags.p;
+    a.work_counter = next_counter(ctx, s);
+    int nl = 0;
+    const char *why = nullptr;
+    cudaError_t e = bdf::launch_deflate(a, ctx->deflate_scratch, ctx->sm_count, s, &nl, &why, max_unit);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail(ctx, BDF_E_CUDA, why ? why : "launch_deflate", e);
+    if (why) return fail(ctx, BDF_E_UNSUPPORTED, why);
+    bdf::JoinArgs j;
+    j.in = (const uint8_t *)ctx->in.p; j.in_off = (const uint64_t *)ctx->in_off.p;
+    j.unit_begin = (const uint32_t *)ctx->u_begin.p; j.tmp = (const uint8_t *)ctx->u_tmp.p;
+    j.tmp_off = (const uint64_t *)ctx->u_tmp_off.p; j.unit_size = (const uint64_t *)ctx->u_size.p;
+    j.unit_status = (const int32_t *)ctx->u_status.p; j.out = (uint8_t *)ctx->out.p;
+    j.out_off = (const uint64_t *)ctx->out_off.p; j.out_size = (uint64_t *)ctx->out_size.p;
+    j.status = (int32_t *)ctx->status.p; j.n = (uint32_t)n; j.level = a.level; j.format = format;
+    unsigned long long want = (n + bdf::JOIN_WARPS - 1) / bdf::JOIN_WARPS;
+    unsigned long long full = (unsigned long long)ctx->sm_count * 16;
+    bdf::deflate_join_kernel<<<(unsigned)(want < full ? want : full), bdf::JOIN_WARPS * 32, 0, s>>>(j);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return BDF_E_OK;
+}
+
 int bdf_compress_batch_host(bdf_ctx *ctx, int level, int format, const uint8_t *in, const uint64_t *in_off,
                             size_t n, uint8_t *out, const uint64_t *out_off, uint64_t *out_size, int32_t *status)
 {
     if (!ctx) return BDF_E_ARG;
     if (bad_format(format)) return fail(ctx, BDF_E_ARG, "unknown format");
+    if (level < 0) return fail(ctx, BDF_E_ARG, "negative level");
     if (n == 0) return BDF_E_OK;
     if (!in || !in_off || !out || !out_off || !out_size || !status) return fail(ctx, BDF_E_ARG, "null pointer");
+    if (n > 0xFFFFFFF0ull) return fail(ctx, BDF_E_ARG, "too many streams");
     size_t in_bytes, out_bytes = 0;
-    if (level >= 1)
-        for (size_t i = 0; i < n; i++)
-            if (in_off[i + 1] - in_off[i] > 65536)
-                return fail(ctx, BDF_E_UNSUPPORTED,
-                            "streams above 65536 bytes are not supported at levels >= 1 in this build");
+    uint64_t max_len = 0;
+    for (size_t i = 0; i < n; i++)
+        if (in_off[i + 1] - in_off[i] > max_len) max_len = in_off[i + 1] - in_off[i];
+    // level 0 needs the unit path only above one chunk (the stored kernel handles any length)
+    const bool chunked = max_len > (level == 0 ? 256u * 1024u : 65536u);
     {
         std::lock_guard<std::mutex> g(ctx->mu);
         CK(cudaSetDevice(ctx->device));
@@ -336,9 +410,16 @@ int bdf_compress_batch_host(bdf_ctx *ctx, int level, int format, const uint8_t *
         CK(cudaMemcpyAsync(ctx->in.p, in, in_bytes, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ctx->in_off.p, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ctx->out_off.p, out_off, n * 8, cudaMemcpyHostToDevice, s));
-        CK(cudaEventRecord(ctx->ev0, s));
+        if (chunked) {
+            rc = compress_chunked_locked(ctx, level, format, in_off, n, s);
+            if (rc) return rc;
+        } else {
+            CK(cudaEventRecord(ctx->ev0, s));
+        }
     }
-    int rc = bdf_compress_batch_device(ctx, level, format, (const uint8_t *)ctx->in.p,
+    int rc = BDF_E_OK;
+    if (!chunked)
+        rc = bdf_compress_batch_device(ctx, level, format, (const uint8_t *)ctx->in.p,
                                        (const uint64_t *)ctx->in_off.p, n, (uint8_t *)ctx->out.p,
                                        (const uint64_t *)ctx->out_off.p, (uint64_t *)ctx->out_size.p,
                                        (int32_t *)ctx->status.p, nullptr);

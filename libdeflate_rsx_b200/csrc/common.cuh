@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "../../include/bdeflate.h"
 
 #define BDF_FULL_MASK 0xFFFFFFFFu

@@ -12,6 +12,7 @@
 #include "deflate_bt.cuh"
 #include "deflate_hc.cuh"
 #include "deflate_l1.cuh"
+#include "gather.cuh"
 
 namespace bdf {
 
@@ -40,11 +41,12 @@ __global__ void __launch_bounds__(L0_WARPS_PER_BLOCK * 32) deflate_stored_kernel
         const uint8_t *in = a.in + a.in_off[idx];
         const uint64_t len = a.in_off[idx + 1] - a.in_off[idx];
         uint8_t *out = a.out + a.out_off[idx];
+        const unsigned uflags = unit_flags_of(a, idx);
         uint64_t op = frame_header(a.format, 0, out, lane);
         // an empty input produces ZERO deflate bytes at level 0 (the block loop never runs, :1408)
         for (uint64_t ip = 0; ip < len;) {
             uint64_t blk = len - ip < 65535 ? len - ip : 65535;
-            unsigned bfinal = ip + 65535 >= len;
+            unsigned bfinal = ip + 65535 >= len && (uflags & UNIT_FINISH);
             if (lane < 5) {
                 uint8_t b = lane == 0 ? (uint8_t)bfinal
                           : lane == 1 ? (uint8_t)blk
@@ -58,17 +60,70 @@ __global__ void __launch_bounds__(L0_WARPS_PER_BLOCK * 32) deflate_stored_kernel
             op += blk;
             ip += blk;
         }
+        if (uflags & UNIT_SYNC) {
+            if (lane < 5) out[op + lane] = lane >= 3 ? 0xFF : 0;
+            op += 5;
+        }
         op = frame_footer(a.format, in, len, out, op, s_crc, s_x2n, lane);
         if (lane == 0) { a.out_size[idx] = op; a.status[idx] = BDF_OK; }
     }
 }
 
-constexpr size_t HC_SCRATCH_PER_CTA = HC_CHAIN_BYTES + (65536 + 64) * sizeof(uint32_t);   // chains + symbol records
 
 // Host-side dispatcher.  *why != nullptr with cudaSuccess means "unsupported".
-inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm_count, cudaStream_t s,
-                                  int *nlaunch, const char **why)
+// ---- chunked streams: Compressor::compress, src/compress/mod.rs:699-772.  An input above 256 KiB
+// is cut into 256 KiB chunks, each compressed by a fresh compressor (units of the deflate kernels,
+// raw DEFLATE, all but the last followed by a sync flush) and the results are concatenated; the
+// zlib / gzip wrapper goes around the whole (:2248-2357).  One warp per stream.
+struct JoinArgs {
+    const uint8_t *in;
+    const uint64_t *in_off;        // n + 1, the streams
+    const uint32_t *unit_begin;    // n + 1: units of stream i are [unit_begin[i], unit_begin[i+1])
+    const uint8_t *tmp;            // unit outputs
+    const uint64_t *tmp_off, *unit_size;
+    const int32_t *unit_status;
+    uint8_t *out;
+    const uint64_t *out_off;
+    uint64_t *out_size;
+    int32_t *status;
+    uint32_t n;
+    int level, format;
+};
+constexpr int JOIN_WARPS = 4;
+__global__ void __launch_bounds__(JOIN_WARPS * 32) deflate_join_kernel(JoinArgs a)
 {
+    __shared__ uint32_t s_crc[4][256];
+    __shared__ uint32_t s_x2n[32];
+    const unsigned lane = lane_id();
+    if (a.format == BDF_GZIP) load_crc_tables_to_smem(s_crc, s_x2n);
+    for (uint32_t idx = blockIdx.x * JOIN_WARPS + (threadIdx.x >> 5); idx < a.n; idx += gridDim.x * JOIN_WARPS) {
+        const uint8_t *in = a.in + a.in_off[idx];
+        const uint64_t len = a.in_off[idx + 1] - a.in_off[idx];
+        uint8_t *out = a.out + a.out_off[idx];
+        const uint64_t hdr = frame_header(a.format, a.level, out, lane);
+        const uint64_t cap = deflate_bound(len);
+        uint64_t op = 0;
+        int st = BDF_OK;
+        for (uint32_t u = a.unit_begin[idx]; u < a.unit_begin[idx + 1]; u++) {
+            if (a.unit_status[u] != BDF_OK) { st = a.unit_status[u]; break; }
+            const uint64_t sz = a.unit_size[u];
+            if (op + sz > cap) { st = BDF_INSUFFICIENT_SPACE; break; }
+            warp_copy_bytes(out + hdr + op, a.tmp + a.tmp_off[u], sz, lane);
+            op += sz;
+        }
+        uint64_t total = 0;
+        if (st == BDF_OK) total = frame_footer(a.format, in, len, out, hdr + op, s_crc, s_x2n, lane);
+        if (lane == 0) { a.status[idx] = st; a.out_size[idx] = total; }
+        __syncwarp();
+    }
+}
+
+// max_len: an upper bound of the entry lengths when the caller knows one (host API), 0 otherwise
+// (device API: the 64 KiB instances run and longer entries get BDF_STREAM_UNSUPPORTED).
+inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm_count, cudaStream_t s,
+                                  int *nlaunch, const char **why, uint64_t max_len = 0)
+{
+    const bool big = max_len > 65536;
     *nlaunch = 0;
     *why = nullptr;
     cudaError_t e;
@@ -78,6 +133,10 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
         deflate_stored_kernel<<<(unsigned)(want < full ? want : full), L0_WARPS_PER_BLOCK * 32, 0, s>>>(a);
         *nlaunch = 1;
         return cudaGetLastError();
+    }
+    if (big && (a.level == 1 || a.level >= 10)) {
+        *why = "streams above 65536 bytes are not supported at levels 1 and 10-12 in this build";
+        return cudaSuccess;
     }
     if (a.level == 1) {
         const size_t smem = sizeof(L1Smem);
@@ -117,12 +176,17 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
         unsigned grid = a.n < full_grid ? a.n : full_grid;
         if (!scratch.hc_ready) {
             *why = "cudaFuncSetAttribute(deflate_hc_kernel)";
-            e = cudaFuncSetAttribute(deflate_hc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaFuncSetAttribute(deflate_hc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(deflate_hc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             scratch.hc_ready = true;
             *why = nullptr;
         }
-        const size_t need = HC_SCRATCH_PER_CTA * (size_t)full_grid;
+        // small instance: one slab per resident CTA (stays L2-resident); big instance: only as many
+        // slabs as CTAs are launched (1.7 MiB each)
+        const size_t per_cta = big ? HcChains<true>::SCRATCH_PER_CTA : HcChains<false>::SCRATCH_PER_CTA;
+        const size_t need = per_cta * (size_t)(big ? grid : full_grid);
         if (scratch.cap < need) {
             if (scratch.p) cudaFree(scratch.p);
             scratch.p = nullptr;
@@ -134,8 +198,9 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
             *why = nullptr;
         }
         a.scratch = scratch.p;
-        a.scratch_stride = HC_SCRATCH_PER_CTA;
-        deflate_hc_kernel<<<grid, HC_THREADS, smem, s>>>(a);
+        a.scratch_stride = per_cta;
+        if (big) deflate_hc_kernel<true><<<grid, HC_THREADS, smem, s>>>(a);
+        else deflate_hc_kernel<false><<<grid, HC_THREADS, smem, s>>>(a);
         *nlaunch = 1;
         return cudaGetLastError();
     }

@@ -21,7 +21,17 @@ struct DeflateArgs {
     uint32_t n;
     int level;
     int format;
+    // Units of a chunked call (Compressor::compress cuts inputs above 256 KiB into 256 KiB chunks,
+    // each through a fresh compressor, src/compress/mod.rs:699-772): bit 0 = this unit ends the
+    // stream (FlushMode::Finish), bit 1 = it is followed by a sync flush (:662-681).  NULL = every
+    // entry is a whole stream (finish, no sync).
+    const uint8_t *unit_flags;
 };
+constexpr unsigned UNIT_FINISH = 1u, UNIT_SYNC = 2u;
+__device__ __forceinline__ unsigned unit_flags_of(const DeflateArgs &a, uint64_t idx)
+{
+    return a.unit_flags ? a.unit_flags[idx] : UNIT_FINISH;
+}
 
 __host__ __device__ inline uint64_t deflate_bound(uint64_t len) { return len + (len / 65535 + 1) * 5 + 10; }
 
@@ -174,6 +184,14 @@ struct BitSink {
         nbits += n;
         __syncwarp();
         if (nbits >= SINK_FLUSH_BITS) flush_words(lane);
+    }
+    // FlushMode::Sync, src/compress/mod.rs:662-681: an empty stored block (000, pad to a byte,
+    // LEN = 0x0000, NLEN = 0xFFFF)
+    __device__ __forceinline__ void sync_marker(unsigned lane)
+    {
+        put1(0, 3, lane);
+        nbits = (nbits + 7u) & ~7u;            // the staging buffer is zero outside [0, nbits)
+        put1(0xFFFF0000u, 32, lane);
     }
     // Bitstream::flush: zero-pad to a byte and store everything.  Returns total bytes or ~0 on overflow.
     __device__ __forceinline__ uint64_t finish(unsigned lane)

@@ -28,9 +28,7 @@ namespace bdf {
 
 constexpr int HC_THREADS = 128;
 constexpr int HC_WARPS = HC_THREADS / 32;
-constexpr uint32_t HC_MAX_LEN = 65536;
 constexpr uint32_t HC_WINDOW = 256;           // positions searched per round (max)
-constexpr uint32_t HC_NOPOS = 0xFFFFu;
 
 // Symbol records written by the parse and consumed by the emitter, in stream order:
 // a literal is its byte value; a match is a length record followed by an offset record.
@@ -59,13 +57,21 @@ struct __align__(16) HcSmem {
 // L2-resident while the stream is being parsed) rather than in shared memory, so that
 // many streams are in flight per SM and the serial parse of one hides behind the
 // chain walks of the others.
-//   head[32768]: bucket -> most recent position, 0xFFFF = empty
-//   link[65536]: position -> distance to the previous same-hash position, 0 = none
+//   head[32768]: bucket -> most recent position, all-ones = empty
+//   link[MAX_LEN]: position -> distance to the previous same-hash position, 0 = none / further
+//                  than 65535 (matchfinder.rs:799-805 stores 0 for those too)
+// Two instances: streams up to 64 KiB (16-bit heads, the BASELINE shapes) and units up to
+// 256 KiB (the chunk size of Compressor::compress, src/compress/mod.rs:699-772; 32-bit heads).
+template <bool BIG>
 struct HcChains {
-    uint16_t *head;
+    using head_t = typename std::conditional<BIG, uint32_t, uint16_t>::type;
+    static constexpr uint32_t MAX_LEN = BIG ? 262144u : 65536u;
+    static constexpr uint32_t NOPOS = BIG ? 0xFFFFFFFFu : 0xFFFFu;
+    static constexpr size_t CHAIN_BYTES = 32768 * sizeof(head_t) + (size_t)MAX_LEN * sizeof(uint16_t);
+    static constexpr size_t SCRATCH_PER_CTA = CHAIN_BYTES + ((size_t)MAX_LEN + 64) * sizeof(uint32_t);   // + symbol records
+    head_t *head;
     uint16_t *link;
 };
-constexpr size_t HC_CHAIN_BYTES = (32768 + 65536) * sizeof(uint16_t);
 
 struct HcParams { unsigned max_depth, nice_len, lazy; };
 __device__ __forceinline__ HcParams hc_params(int level)
@@ -87,7 +93,8 @@ __device__ __forceinline__ HcParams hc_params(int level)
 
 // Insert positions [from, to) (warp 0, all lanes).  Positions with fewer than
 // 3 bytes left are never inserted (matchfinder.rs:765,1021).
-__device__ __forceinline__ void hc_insert_range(const HcChains &ch, const uint8_t *in, uint32_t len, uint32_t from,
+template <class CH>
+__device__ __forceinline__ void hc_insert_range(const CH &ch, const uint8_t *in, uint32_t len, uint32_t from,
                                                 uint32_t to, unsigned lane)
 {
     for (uint32_t base = from; base < to; base += 32) {
@@ -99,10 +106,10 @@ __device__ __forceinline__ void hc_insert_range(const HcChains &ch, const uint8_
         const unsigned lower = peers & lanemask_lt();
         if (ok) {
             uint32_t prev = lower ? base + (31 - __clz(lower)) : ch.head[h];
-            ch.link[p] = prev == HC_NOPOS ? 0 : (uint16_t)(p - prev);   // distance <= 65535 always fits
+            ch.link[p] = (prev == CH::NOPOS || p - prev > 0xFFFFu) ? 0 : (uint16_t)(p - prev);
         }
         __syncwarp();
-        if (ok && (peers >> lane) == 1u) ch.head[h] = (uint16_t)p;
+        if (ok && (peers >> lane) == 1u) ch.head[h] = (typename CH::head_t)p;
         __syncwarp();
     }
 }
@@ -130,7 +137,8 @@ __device__ __forceinline__ unsigned prefix_len_bytes(const uint8_t *a, const uin
 }
 
 // find_match_impl without the insertion (already done): walk the chain of p.
-__device__ __forceinline__ void hc_search(const HcChains &ch, const uint8_t *in, uint32_t len, uint32_t p,
+template <class CH>
+__device__ __forceinline__ void hc_search(const CH &ch, const uint8_t *in, uint32_t len, uint32_t p,
                                           const HcParams &prm, unsigned &out_len, unsigned &out_off)
 {
     out_len = 0; out_off = 0;
@@ -260,18 +268,20 @@ __device__ void hc_prepare_header(S &sm, unsigned &nlit, unsigned &noff, unsigne
     while (npre > 4 && sm.pre_len[perm[npre - 1]] == 0) npre--;
 }
 
+template <bool BIG>
 __global__ void __launch_bounds__(HC_THREADS) deflate_hc_kernel(DeflateArgs a)
 {
+    using CH = HcChains<BIG>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HcSmem &sm = *reinterpret_cast<HcSmem *>(smem_raw);
     __shared__ unsigned long long s_idx;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const HcParams prm = hc_params(a.level);
     uint8_t *slab = static_cast<uint8_t *>(a.scratch) + a.scratch_stride * blockIdx.x;
-    HcChains ch;
-    ch.head = reinterpret_cast<uint16_t *>(slab);
-    ch.link = ch.head + 32768;
-    uint32_t *syms = reinterpret_cast<uint32_t *>(slab + HC_CHAIN_BYTES);
+    CH ch;
+    ch.head = reinterpret_cast<typename CH::head_t *>(slab);
+    ch.link = reinterpret_cast<uint16_t *>(ch.head + 32768);
+    uint32_t *syms = reinterpret_cast<uint32_t *>(slab + CH::CHAIN_BYTES);
     if (a.format == BDF_GZIP) load_crc_tables_to_smem(sm.crc, sm.x2n);
 
     for (;;) {
@@ -283,12 +293,14 @@ __global__ void __launch_bounds__(HC_THREADS) deflate_hc_kernel(DeflateArgs a)
         const uint8_t *in = a.in + a.in_off[idx];
         const uint64_t len64 = a.in_off[idx + 1] - a.in_off[idx];
         uint8_t *out = a.out + a.out_off[idx];
-        if (len64 > HC_MAX_LEN) {
+        const unsigned uflags = unit_flags_of(a, idx);
+        if (len64 > CH::MAX_LEN) {
             if (tid == 0) { a.status[idx] = BDF_STREAM_UNSUPPORTED; a.out_size[idx] = 0; }
             continue;
         }
         const uint32_t len = (uint32_t)len64;
-        for (unsigned i = tid; i < 32768 / 8; i += HC_THREADS) reinterpret_cast<uint4 *>(ch.head)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+        for (unsigned i = tid; i < 32768 * sizeof(typename CH::head_t) / 16; i += HC_THREADS)
+            reinterpret_cast<uint4 *>(ch.head)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
         unsigned hdr = 0;
         BitSink bs;
         if (warp == 0) {
@@ -430,7 +442,7 @@ __global__ void __launch_bounds__(HC_THREADS) deflate_hc_kernel(DeflateArgs a)
                 npre = __shfl_sync(BDF_FULL_MASK, npre, 0);
                 nitems = __shfl_sync(BDF_FULL_MASK, nitems, 0);
                 __syncwarp();
-                const bool is_final = p >= len;
+                const bool is_final = p >= len && (uflags & UNIT_FINISH);
                 bs.put1((is_final ? 1u : 0u) | (2u << 1), 3, lane);
                 bs.put1((nlit_syms - 257) | ((noff_syms - 1) << 5) | ((npre - 4) << 10), 14, lane);
                 {
@@ -479,6 +491,7 @@ __global__ void __launch_bounds__(HC_THREADS) deflate_hc_kernel(DeflateArgs a)
             __syncthreads();
         } while (p < len);
         if (warp == 0) {
+            if (uflags & UNIT_SYNC) bs.sync_marker(lane);
             uint64_t sz = bs.finish(lane);
             int st = BDF_OK;
             if (sz == ~0ull) { st = BDF_INSUFFICIENT_SPACE; sz = 0; }

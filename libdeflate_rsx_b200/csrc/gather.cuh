@@ -19,31 +19,33 @@ struct GatherArgs {
 
 constexpr int GATHER_WARPS = 4;
 
+// d[0..len) = s[0..len), one warp, 16-byte destination-aligned chunks, source realigned with PRMT
+__device__ __forceinline__ void warp_copy_bytes(uint8_t *d, const uint8_t *s, uint64_t len, unsigned lane)
+{
+    uint64_t head = (16u - (reinterpret_cast<uintptr_t>(d) & 15u)) & 15u;
+    if (head > len) head = len;
+    if (lane < head) d[lane] = s[lane];
+    const uint64_t nbody = (len - head) >> 4;
+    const uint8_t *sb = s + head;
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(sb) & 3u);
+    const uint32_t sel = 0x3210u + 0x1111u * sh;
+    for (uint64_t c = lane; c < nbody; c += 32) {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(sb + 16 * c - sh);
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = sh ? w[4] : 0u;
+        *reinterpret_cast<uint4 *>(d + head + 16 * c) =
+            make_uint4(__byte_perm(w0, w1, sel), __byte_perm(w1, w2, sel), __byte_perm(w2, w3, sel),
+                       __byte_perm(w3, w4, sel));
+    }
+    const uint64_t done = head + 16 * nbody;
+    if (done + lane < len) d[done + lane] = s[done + lane];
+}
+
 __global__ void __launch_bounds__(GATHER_WARPS * 32) gather_kernel(GatherArgs a)
 {
     const unsigned lane = lane_id();
     for (uint64_t i = (uint64_t)blockIdx.x * GATHER_WARPS + threadIdx.x / 32; i < a.n;
-         i += (uint64_t)gridDim.x * GATHER_WARPS) {
-        const uint8_t *s = a.src + a.src_off[i];
-        uint8_t *d = a.dst + a.dst_off[i];
-        const uint64_t len = a.size[i];
-        uint64_t head = (16u - (reinterpret_cast<uintptr_t>(d) & 15u)) & 15u;
-        if (head > len) head = len;
-        if (lane < head) d[lane] = s[lane];
-        const uint64_t nbody = (len - head) >> 4;
-        const uint8_t *sb = s + head;
-        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(sb) & 3u);
-        const uint32_t sel = 0x3210u + 0x1111u * sh;
-        for (uint64_t c = lane; c < nbody; c += 32) {
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(sb + 16 * c - sh);
-            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = sh ? w[4] : 0u;
-            *reinterpret_cast<uint4 *>(d + head + 16 * c) =
-                make_uint4(__byte_perm(w0, w1, sel), __byte_perm(w1, w2, sel), __byte_perm(w2, w3, sel),
-                           __byte_perm(w3, w4, sel));
-        }
-        const uint64_t done = head + 16 * nbody;
-        if (done + lane < len) d[done + lane] = s[done + lane];
-    }
+         i += (uint64_t)gridDim.x * GATHER_WARPS)
+        warp_copy_bytes(a.dst + a.dst_off[i], a.src + a.src_off[i], a.size[i], lane);
 }
 
 }  // namespace bdf

@@ -70,12 +70,47 @@ def test_compress_byte_identical_to_oracle(engine):
                     assert zlib.decompress(g, WBITS[fmt]) == s
 
 
-def test_oversize_streams_fail_loudly(engine):
-    # levels >= 1 are limited to 64 KiB streams in this build: an error, never a silent empty result
+def large_inputs():
+    t = corpus.text_stream(6, 65536)
+    return [
+        corpus.text_stream(6, 70000),                                   # one unit above 64 KiB
+        (t * 5)[:262144], (t * 5)[:262145],                             # exactly one chunk / one byte more
+        (corpus.binary_stream(4) * 10)[:600001],                        # three chunks
+        b"".join(corpus.corpus_a_stream(k) for k in range(16)),         # 1 MiB of corpus A: four chunks
+        corpus.lowentropy_stream(2) + corpus.text_stream(3) * 3,        # 256 KiB: stays one unit
+        b"short one in the same batch",
+    ]
+
+
+LARGE_LEVELS = [0, 2, 6, 9]
+
+
+def test_large_streams_chunked_byte_identical(engine):
+    """Streams above 64 KiB (one 256 KiB unit) and above 256 KiB (chunks joined by sync flushes,
+    src/compress/mod.rs:699-772): byte-identical to the oracle, and valid under system zlib."""
+    ins = large_inputs()
+    for fmt in (0, 1, 2):
+        for level in LARGE_LEVELS:
+            got = engine.BatchCompressor(level, format=fmt).compress_batch(ins)
+            for g, s in zip(got, ins):
+                exp = o.compress(s, level, fmt)
+                assert g == (exp if exp is not None else b""), (fmt, level, len(s), len(g), len(exp or b""))
+                if exp is not None:       # level 0 above 256 KiB overflows its bound (sync markers): in-band failure
+                    assert zlib.decompress(g, WBITS[fmt]) == s
+    # and back through the batch decompressor
+    comp = engine.BatchCompressor(6, format=2).compress_batch(ins)
+    assert engine.BatchDecompressor(format=2).decompress_batch(comp, [len(s) for s in ins]) == ins
+
+
+def test_large_streams_unsupported_levels_fail_loudly(engine):
+    # levels not yet built for units above 64 KiB: an error, never a silent empty result
     big = corpus.text_stream(6, 70000)
-    with pytest.raises(engine.BdfError):
-        engine.BatchCompressor(6).compress_batch([big])
-    assert zlib.decompress(engine.BatchCompressor(0).compress_batch([big])[0], -15) == big
+    for level in [l for l in range(1, 13) if l not in LARGE_LEVELS]:
+        try:
+            got = engine.BatchCompressor(level).compress_batch([big])
+        except engine.BdfError:
+            continue
+        assert got == [o.compress(big, level)], level
 
 
 def test_compress_failure_is_in_band(engine):
