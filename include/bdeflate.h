@@ -117,10 +117,13 @@ int bdf_decompress_batch_host(bdf_ctx *ctx, int format, const uint8_t *in,
  * out + out_off[i]; a stream whose encoding does not fit fails with
  * BDF_INSUFFICIENT_SPACE and out_size[i] = 0 — the reference has no
  * stored-block fallback (src/compress/mod.rs:641-644).
- * Limit of this build: at levels >= 1
- * a stream longer than 65536 bytes is not compressed — the *_host call returns
- * BDF_E_UNSUPPORTED before doing any work, the *_device call (which cannot see
- * the lengths) sets status[i] = BDF_STREAM_UNSUPPORTED for that stream.
+ * Stream length: the *_host call takes any length.  Streams above 64 KiB run through the
+ * 256 KiB kernel instances; streams above 256 KiB are cut into 256 KiB chunks, each compressed
+ * by a fresh compressor, all but the last followed by a sync flush, like Compressor::compress
+ * (src/compress/mod.rs:699-772) — byte-identical to the reference's output for every length.
+ * The *_device call cannot see the lengths without synchronising: it runs the 64 KiB instances
+ * and sets status[i] = BDF_STREAM_UNSUPPORTED for a longer stream (level 0 takes any length up
+ * to 256 KiB there).
  */
 int bdf_compress_batch_device(bdf_ctx *ctx, int level, int format,
                               const uint8_t *in, const uint64_t *in_off, size_t n,

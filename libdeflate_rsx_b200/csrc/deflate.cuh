@@ -134,10 +134,6 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
         *nlaunch = 1;
         return cudaGetLastError();
     }
-    if (big && (a.level == 1 || a.level >= 10)) {
-        *why = "streams above 65536 bytes are not supported at levels 1 and 10-12 in this build";
-        return cudaSuccess;
-    }
     if (a.level == 1) {
         const size_t smem = sizeof(L1Smem);
         static int l1_ctas_per_sm = 0;
@@ -148,7 +144,8 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
         const unsigned long long full = (unsigned long long)sm_count * l1_ctas_per_sm;
         const unsigned long long want = ((unsigned long long)a.n + L1_WARPS - 1) / L1_WARPS;
         const unsigned grid = (unsigned)(want < full ? want : full);
-        const size_t need = L1_TABLE_BYTES * L1_WARPS * (size_t)full;
+        const size_t per_warp = big ? L1Cfg<true>::TABLE_BYTES : L1Cfg<false>::TABLE_BYTES;
+        const size_t need = per_warp * L1_WARPS * (size_t)(big ? grid : full);
         if (scratch.cap < need) {
             if (scratch.p) cudaFree(scratch.p);
             scratch.p = nullptr;
@@ -160,8 +157,9 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
             *why = nullptr;
         }
         a.scratch = scratch.p;
-        a.scratch_stride = L1_TABLE_BYTES;
-        deflate_l1_kernel<<<grid, L1_WARPS * 32, smem, s>>>(a);
+        a.scratch_stride = per_warp;
+        if (big) deflate_l1_kernel<true><<<grid, L1_WARPS * 32, smem, s>>>(a);
+        else deflate_l1_kernel<false><<<grid, L1_WARPS * 32, smem, s>>>(a);
         *nlaunch = 1;
         return cudaGetLastError();
     }
@@ -210,10 +208,12 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
             const char *env = getenv("BDF_BT_THREADS_PER_SM");
             bt_threads_per_sm = env && atoi(env) > 0 ? atoi(env) : 128;
         }
-        const unsigned long long full = (unsigned long long)sm_count * bt_threads_per_sm / BT_THREADS;
+        // the 256 KiB instance needs 4.3 MiB per thread: a quarter of the threads
+        const unsigned long long full = (unsigned long long)sm_count * (big ? bt_threads_per_sm / 4 : bt_threads_per_sm) / BT_THREADS;
         const unsigned long long want = ((unsigned long long)a.n + BT_THREADS - 1) / BT_THREADS;
         const unsigned grid = (unsigned)(want < full ? want : full);
-        const size_t need = BT_SLAB_BYTES * (size_t)grid * BT_THREADS;
+        const size_t per_thread = big ? BtTables<true>::SLAB_BYTES : BtTables<false>::SLAB_BYTES;
+        const size_t need = per_thread * (size_t)grid * BT_THREADS;
         if (scratch.cap < need) {
             if (scratch.p) cudaFree(scratch.p);
             scratch.p = nullptr;
@@ -225,8 +225,9 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
             *why = nullptr;
         }
         a.scratch = scratch.p;
-        a.scratch_stride = BT_SLAB_BYTES;
-        deflate_bt_kernel<<<grid, BT_THREADS, 0, s>>>(a);
+        a.scratch_stride = per_thread;
+        if (big) deflate_bt_kernel<true><<<grid, BT_THREADS, 0, s>>>(a);
+        else deflate_bt_kernel<false><<<grid, BT_THREADS, 0, s>>>(a);
         *nlaunch = 1;
         return cudaGetLastError();
     }

@@ -2,7 +2,8 @@
 //
 // Replaces, for the batch path, the reference's BtMatchFinder
 // (src/compress/matchfinder.rs:1308-1776) and compress_near_optimal_block
-// (src/compress/mod.rs:1586-1773, costs :2209-2234) for inputs up to 65536 bytes.
+// (src/compress/mod.rs:1586-1773, costs :2209-2234) for inputs up to 65536 bytes, and a second
+// instance for units of up to 256 KiB.
 //
 // Both the tree updates and the forward DP are serial per stream and touch
 // ~1 MiB of state, so this tier goes the other way from levels 1-9: ONE THREAD
@@ -19,33 +20,38 @@
 
 namespace bdf {
 
-constexpr uint32_t BT_MAX_LEN = 65536;
-constexpr uint16_t BT_NONE = 0xFFFFu;
 constexpr int BT_THREADS = 32;
 
-// per-thread slab layout (bytes)
-constexpr size_t BT_OFF_HASH3 = 0;                                  // u16[65536][2]
-constexpr size_t BT_OFF_HASH4 = BT_OFF_HASH3 + 65536 * 2 * 2;       // u16[65536]
-constexpr size_t BT_OFF_CHILD = BT_OFF_HASH4 + 65536 * 2;           // u16[32768][2]
-constexpr size_t BT_OFF_COST = BT_OFF_CHILD + 32768 * 2 * 2;        // u32[65537 (+pad)]
-constexpr size_t BT_OFF_PATH = BT_OFF_COST + 65600 * 4;             // u32[65537 (+pad)]
-constexpr size_t BT_OFF_SYMS = BT_OFF_PATH + 65600 * 4;             // u32[65536 + 64]
-constexpr size_t BT_SLAB_BYTES = BT_OFF_SYMS + (65536 + 64) * 4;
-
+// Per-thread slab.  Two instances: streams up to 64 KiB (16-bit positions, the BASELINE shapes)
+// and units up to 256 KiB (the chunk size of Compressor::compress; 32-bit positions like the
+// reference's i32 tables).
+template <bool BIG>
 struct BtTables {
-    uint16_t *hash3;   // [h][2]
-    uint16_t *hash4;
-    uint16_t *child;   // [pos & 32767][2]
+    using pos_t = typename std::conditional<BIG, uint32_t, uint16_t>::type;
+    static constexpr uint32_t MAX_LEN = BIG ? 262144u : 65536u;
+    static constexpr uint32_t NONE = BIG ? 0xFFFFFFFFu : 0xFFFFu;
+    // slab layout (bytes)
+    static constexpr size_t OFF_HASH3 = 0;                                              // pos_t[65536][2]
+    static constexpr size_t OFF_HASH4 = OFF_HASH3 + 65536 * 2 * sizeof(pos_t);          // pos_t[65536]
+    static constexpr size_t OFF_CHILD = OFF_HASH4 + 65536 * sizeof(pos_t);              // pos_t[32768][2]
+    static constexpr size_t OFF_COST = OFF_CHILD + 32768 * 2 * sizeof(pos_t);           // u32[MAX_LEN + 1 (+pad)]
+    static constexpr size_t OFF_PATH = OFF_COST + ((size_t)MAX_LEN + 64) * 4;           // u32[MAX_LEN + 1 (+pad)]
+    static constexpr size_t OFF_SYMS = OFF_PATH + ((size_t)MAX_LEN + 64) * 4;           // u32[MAX_LEN + 64]
+    static constexpr size_t SLAB_BYTES = OFF_SYMS + ((size_t)MAX_LEN + 64) * 4;
+    static constexpr size_t HASH_BYTES = 65536 * 3 * sizeof(pos_t);                     // hash3 and hash4 are adjacent
+    pos_t *hash3;   // [h][2]
+    pos_t *hash4;
+    pos_t *child;   // [pos & 32767][2]
+    static __device__ __forceinline__ int pos(pos_t v) { return v == (pos_t)NONE ? -1 : (int)v; }
 };
 
-__device__ __forceinline__ int bt_pos(uint16_t v) { return v == BT_NONE ? -1 : (int)v; }
-
 // BtMatchFinder::reset (:1327-1331): hash tables only, child_tab is left as it is
-__device__ void bt_reset(BtTables &b)
+template <class BT>
+__device__ void bt_reset(BT &b)
 {
     uint4 *p = reinterpret_cast<uint4 *>(b.hash3);
     const uint4 ff = make_uint4(~0u, ~0u, ~0u, ~0u);
-    for (unsigned i = 0; i < (65536 * 2 * 2 + 65536 * 2) / 16; i++) p[i] = ff;    // hash3 and hash4 are adjacent
+    for (unsigned i = 0; i < BT::HASH_BYTES / 16; i++) p[i] = ff;
 }
 
 struct BtVisitor {
@@ -68,7 +74,8 @@ __device__ __forceinline__ void bt_on_match(BtVisitor &v, unsigned len, unsigned
 }
 
 // advance_one_byte_generic, src/compress/matchfinder.rs:1344-1463 (base_offset == 0)
-__device__ void bt_advance_one_byte(BtTables &b, const uint8_t *d, uint32_t n, uint32_t pos, unsigned max_depth,
+template <class BT>
+__device__ void bt_advance_one_byte(BT &b, const uint8_t *d, uint32_t n, uint32_t pos, unsigned max_depth,
                                     unsigned nice_len, BtVisitor &v)
 {
     if (pos + 4 > n) return;
@@ -78,22 +85,22 @@ __device__ void bt_advance_one_byte(BtTables &b, const uint8_t *d, uint32_t n, u
     const uint32_t h3 = (v3 * 0x1E35A7BDu) >> 16;
     const uint32_t h4 = (val * 0x1E35A7BDu) >> 16;
     const int self = (int)pos;
-    const uint16_t r3 = b.hash3[2 * h3];
-    const int c3 = bt_pos(r3);
-    b.hash3[2 * h3] = (uint16_t)pos;
-    const int c3b = bt_pos(b.hash3[2 * h3 + 1]);
+    const typename BT::pos_t r3 = b.hash3[2 * h3];
+    const int c3 = BT::pos(r3);
+    b.hash3[2 * h3] = (typename BT::pos_t)pos;
+    const int c3b = BT::pos(b.hash3[2 * h3 + 1]);
     b.hash3[2 * h3 + 1] = r3;
     const int cutoff = self - 32768;
     if (c3 != -1 && c3 > cutoff) {
         if (ld24(d + c3) == v3) bt_on_hash3(v, 3, (unsigned)(self - c3));
         else if (c3b != -1 && c3b > cutoff && ld24(d + c3b) == v3) bt_on_hash3(v, 3, (unsigned)(self - c3b));
     }
-    int cur = bt_pos(b.hash4[h4]);
-    b.hash4[h4] = (uint16_t)pos;
+    int cur = BT::pos(b.hash4[h4]);
+    b.hash4[h4] = (typename BT::pos_t)pos;
     const unsigned me = pos & 32767u;
     if (cur == -1 || cur <= cutoff) {
-        b.child[2 * me] = BT_NONE;
-        b.child[2 * me + 1] = BT_NONE;
+        b.child[2 * me] = (typename BT::pos_t)BT::NONE;
+        b.child[2 * me + 1] = (typename BT::pos_t)BT::NONE;
         return;
     }
     unsigned depth_left = max_depth;
@@ -110,17 +117,17 @@ __device__ void bt_advance_one_byte(BtTables &b, const uint8_t *d, uint32_t n, u
             return;
         }
         if (m[len] < src[len]) {
-            b.child[lt_slot] = (uint16_t)cur;
+            b.child[lt_slot] = (typename BT::pos_t)cur;
             lt_slot = 2 * ci + 1;
-            cur = bt_pos(b.child[2 * ci + 1]);
+            cur = BT::pos(b.child[2 * ci + 1]);
         } else {
-            b.child[gt_slot] = (uint16_t)cur;
+            b.child[gt_slot] = (typename BT::pos_t)cur;
             gt_slot = 2 * ci;
-            cur = bt_pos(b.child[2 * ci]);
+            cur = BT::pos(b.child[2 * ci]);
         }
         if (cur == -1 || cur <= cutoff || --depth_left == 0) {
-            b.child[lt_slot] = BT_NONE;
-            b.child[gt_slot] = BT_NONE;
+            b.child[lt_slot] = (typename BT::pos_t)BT::NONE;
+            b.child[gt_slot] = (typename BT::pos_t)BT::NONE;
             return;
         }
     }
@@ -205,9 +212,10 @@ __device__ void bt_write_block(BtLocal &L, ThreadBits &bs, const uint32_t *syms,
 }
 
 // compress_near_optimal_block, src/compress/mod.rs:1586-1773.  Returns bytes processed.
-__device__ uint32_t bt_near_optimal_block(BtTables &bt, BtLocal &L, uint32_t *cost, uint32_t *path, uint32_t *syms,
+template <class BT>
+__device__ uint32_t bt_near_optimal_block(BT &bt, BtLocal &L, uint32_t *cost, uint32_t *path, uint32_t *syms,
                                           const uint8_t *in, uint32_t n, uint32_t start, ThreadBits &bs,
-                                          unsigned max_depth, unsigned nice_len)
+                                          unsigned max_depth, unsigned nice_len, bool finish)
 {
     // pass 1: greedy parse with the binary tree -> split point and first costs
     for (int i = 0; i < 288; i++) L.litlen_freq[i] = 0;
@@ -240,7 +248,7 @@ __device__ uint32_t bt_near_optimal_block(BtTables &bt, BtLocal &L, uint32_t *co
     }
     const uint32_t done = p - start;
     const uint8_t *blk = in + start;
-    const bool is_final = start + done >= n;
+    const bool is_final = start + done >= n && finish;
     L.litlen_freq[256]++;
     make_huffman_code_serial(288, 14, L.litlen_freq, L.litlen_len, L.litlen_code, L.scratch);
     make_huffman_code_serial(32, 15, L.offset_freq, L.offset_len, L.offset_code, L.scratch);
@@ -313,17 +321,19 @@ __device__ uint32_t bt_near_optimal_block(BtTables &bt, BtLocal &L, uint32_t *co
     return done;
 }
 
+template <bool BIG>
 __global__ void __launch_bounds__(BT_THREADS) deflate_bt_kernel(DeflateArgs a)
 {
+    using BT = BtTables<BIG>;
     const unsigned gtid = blockIdx.x * BT_THREADS + threadIdx.x;
     uint8_t *slab = static_cast<uint8_t *>(a.scratch) + a.scratch_stride * gtid;
-    BtTables bt;
-    bt.hash3 = reinterpret_cast<uint16_t *>(slab + BT_OFF_HASH3);
-    bt.hash4 = reinterpret_cast<uint16_t *>(slab + BT_OFF_HASH4);
-    bt.child = reinterpret_cast<uint16_t *>(slab + BT_OFF_CHILD);
-    uint32_t *cost = reinterpret_cast<uint32_t *>(slab + BT_OFF_COST);
-    uint32_t *path = reinterpret_cast<uint32_t *>(slab + BT_OFF_PATH);
-    uint32_t *syms = reinterpret_cast<uint32_t *>(slab + BT_OFF_SYMS);
+    BT bt;
+    bt.hash3 = reinterpret_cast<typename BT::pos_t *>(slab + BT::OFF_HASH3);
+    bt.hash4 = reinterpret_cast<typename BT::pos_t *>(slab + BT::OFF_HASH4);
+    bt.child = reinterpret_cast<typename BT::pos_t *>(slab + BT::OFF_CHILD);
+    uint32_t *cost = reinterpret_cast<uint32_t *>(slab + BT::OFF_COST);
+    uint32_t *path = reinterpret_cast<uint32_t *>(slab + BT::OFF_PATH);
+    uint32_t *syms = reinterpret_cast<uint32_t *>(slab + BT::OFF_SYMS);
     BtLocal L;
     const unsigned max_depth = a.level == 10 ? 35 : a.level == 11 ? 100 : 300;
     const unsigned nice_len = a.level == 10 ? 75 : a.level == 11 ? 150 : 258;
@@ -333,7 +343,8 @@ __global__ void __launch_bounds__(BT_THREADS) deflate_bt_kernel(DeflateArgs a)
         const uint8_t *in = a.in + a.in_off[idx];
         const uint64_t len64 = a.in_off[idx + 1] - a.in_off[idx];
         uint8_t *out = a.out + a.out_off[idx];
-        if (len64 > BT_MAX_LEN) { a.status[idx] = BDF_STREAM_UNSUPPORTED; a.out_size[idx] = 0; continue; }
+        if (len64 > BT::MAX_LEN) { a.status[idx] = BDF_STREAM_UNSUPPORTED; a.out_size[idx] = 0; continue; }
+        const unsigned uflags = unit_flags_of(a, idx);
         const uint32_t len = (uint32_t)len64;
         // framing header (compress_zlib / compress_gzip, src/compress/mod.rs:2248-2357)
         unsigned hdr = 0;
@@ -352,8 +363,16 @@ __global__ void __launch_bounds__(BT_THREADS) deflate_bt_kernel(DeflateArgs a)
         bt_reset(bt);
         uint32_t p = 0;
         do {
-            p += bt_near_optimal_block(bt, L, cost, path, syms, in, len, p, bs, max_depth, nice_len);
+            p += bt_near_optimal_block(bt, L, cost, path, syms, in, len, p, bs, max_depth, nice_len,
+                                       (uflags & UNIT_FINISH) != 0);
         } while (p < len);
+        if (uflags & UNIT_SYNC) {
+            // FlushMode::Sync, src/compress/mod.rs:662-681
+            bs.put(0, 3);
+            bs.finish();
+            bs.put(0x0000u, 16);
+            bs.put(0xFFFFu, 16);
+        }
         bs.finish();
         int st = BDF_OK;
         uint64_t sz = bs.pos;

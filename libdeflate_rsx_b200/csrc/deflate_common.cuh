@@ -185,6 +185,23 @@ struct BitSink {
         __syncwarp();
         if (nbits >= SINK_FLUSH_BITS) flush_words(lane);
     }
+    // bit position of the next bit, counted from the start of the stream
+    __device__ __forceinline__ uint64_t bitpos() const { return flushed * 8 + nbits; }
+    // sets one bit that has already been put (a BFINAL bit that is only known at the end of its
+    // block); the byte is either still in the staging buffer or already in global memory
+    __device__ __forceinline__ void set_bit(uint64_t at, unsigned lane)
+    {
+        __syncwarp();
+        if (lane == 0 && !overflow) {
+            if (at >= flushed * 8) {
+                const uint32_t r = (uint32_t)(at - flushed * 8);
+                buf[r >> 5] |= 1u << (r & 31u);
+            } else {
+                out[at >> 3] |= (uint8_t)(1u << (at & 7u));
+            }
+        }
+        __syncwarp();
+    }
     // FlushMode::Sync, src/compress/mod.rs:662-681: an empty stored block (000, pad to a byte,
     // LEN = 0x0000, NLEN = 0xFFFF)
     __device__ __forceinline__ void sync_marker(unsigned lane)

@@ -2,7 +2,9 @@
 //
 // Replaces compress_greedy_block's level-1 branch with HtMatchFinder
 // (reference src/compress/mod.rs:1499-1583, src/compress/matchfinder.rs:1139-1231)
-// for inputs of at most 65536 bytes (one block, no split statistics, :1505-1529).
+// Inputs of at most 65536 bytes are one block without split statistics (:1505-1529); longer
+// ones (units of up to 256 KiB, the second kernel instance) run the block-split heuristic
+// while staying static-Huffman (:1531-1564).
 //
 // The parse is inherently serial because only positions where find_match is
 // CALLED enter the table (skip_positions is a no-op, :1231).  One warp owns a
@@ -17,20 +19,30 @@
 
 namespace bdf {
 
-constexpr uint32_t L1_MAX_LEN = 65536;
-constexpr uint32_t L1_EMPTY = 0xFFFFu;
-
 constexpr int L1_WARPS = 4;                      // streams per CTA
-constexpr size_t L1_TABLE_BYTES = 32768 * sizeof(uint16_t);
 
-// The 64 KiB hash table of each stream (last position per bucket, 0xFFFF = empty) lives in
-// a per-warp global slab that stays L2-resident while the stream is parsed: in shared
-// memory it would cap the SM at three streams, and this parse is a chain of dependent
-// probes that only many streams in flight can hide.
+// The hash table of each stream (last position per bucket, all-ones = empty; 16-bit positions
+// for the 64 KiB instance, 32-bit for the 256 KiB one) lives in a per-warp global slab that
+// stays L2-resident while the stream is parsed: in shared memory it would cap the SM at three
+// streams, and this parse is a chain of dependent probes that only many streams in flight can hide.
+template <bool BIG>
+struct L1Cfg {
+    using pos_t = typename std::conditional<BIG, uint32_t, uint16_t>::type;
+    static constexpr uint32_t MAX_LEN = BIG ? 262144u : 65536u;
+    static constexpr uint32_t EMPTY = BIG ? 0xFFFFFFFFu : 0xFFFFu;
+    static constexpr size_t TABLE_BYTES = 32768 * sizeof(pos_t);
+};
+
+struct L1SplitStats {                            // BlockSplitStats, src/compress/mod.rs:271-416
+    uint32_t new_obs[14], obs[14];
+    uint32_t num_new, num_obs;
+};
+
 struct __align__(16) L1Smem {
     uint32_t sink[L1_WARPS][SINK_WORDS];
     uint32_t crc[4][256];
     uint32_t x2n[32];
+    L1SplitStats st[L1_WARPS];
 };
 
 // static Huffman codes (RFC 1951 3.2.6), returned bit-reversed for the LSB-first stream
@@ -57,13 +69,17 @@ __device__ __forceinline__ void static_off_code(unsigned off, uint32_t &bits, ui
     n = 5 + extra;
 }
 
+template <bool BIG>
 __global__ void __launch_bounds__(L1_WARPS * 32) deflate_l1_kernel(DeflateArgs a)
 {
+    using CFG = L1Cfg<BIG>;
+    using pos_t = typename CFG::pos_t;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     L1Smem &sm = *reinterpret_cast<L1Smem *>(smem_raw);
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    uint16_t *table = reinterpret_cast<uint16_t *>(static_cast<uint8_t *>(a.scratch) +
-                                                   a.scratch_stride * (blockIdx.x * L1_WARPS + warp));
+    pos_t *table = reinterpret_cast<pos_t *>(static_cast<uint8_t *>(a.scratch) +
+                                             a.scratch_stride * (blockIdx.x * L1_WARPS + warp));
+    L1SplitStats &st = sm.st[warp];
     if (a.format == BDF_GZIP) load_crc_tables_to_smem(sm.crc, sm.x2n);
     for (;;) {
         unsigned long long idx = 0;
@@ -73,16 +89,26 @@ __global__ void __launch_bounds__(L1_WARPS * 32) deflate_l1_kernel(DeflateArgs a
         const uint8_t *in = a.in + a.in_off[idx];
         const uint64_t len64 = a.in_off[idx + 1] - a.in_off[idx];
         uint8_t *out = a.out + a.out_off[idx];
-        if (len64 > L1_MAX_LEN) {
+        if (len64 > CFG::MAX_LEN) {
             if (lane == 0) { a.status[idx] = BDF_STREAM_UNSUPPORTED; a.out_size[idx] = 0; }
             continue;
         }
         const uint32_t len = (uint32_t)len64;
-        for (unsigned i = lane; i < 32768 / 8; i += 32) reinterpret_cast<uint4 *>(table)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+        const unsigned uflags = unit_flags_of(a, idx);
+        const bool split = BIG && len > 65536;       // :1505: at most 64 KiB is one block, no statistics
+        for (unsigned i = lane; i < CFG::TABLE_BYTES / 16; i += 32) reinterpret_cast<uint4 *>(table)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
         const unsigned hdr = frame_header(a.format, 1, out, lane);
         BitSink bs;
         bs.init(sm.sink[warp], out + hdr, deflate_bound(len), lane);
-        bs.put1(3, 3, lane);                     // BFINAL = 1, BTYPE = 01
+        // BTYPE = 01; BFINAL of a block that may still be split is written as 0 and set at the end
+        uint64_t bfinal_at = bs.bitpos();
+        bs.put1((!split && (uflags & UNIT_FINISH) ? 1u : 0u) | 2u, 3, lane);
+        uint32_t block_start = 0;
+        if (split) {
+            if (lane < 14) { st.new_obs[lane] = 0; st.obs[lane] = 0; }
+            if (lane == 0) { st.num_new = 0; st.num_obs = 0; }
+            __syncwarp();
+        }
 
         uint32_t pos = 0;
         while (pos < len) {
@@ -92,24 +118,81 @@ __global__ void __launch_bounds__(L1_WARPS * 32) deflate_l1_kernel(DeflateArgs a
             if (hashable) { v = ld24(in + p); h = hash3(v); }
             const unsigned peers = __match_any_sync(BDF_FULL_MASK, h);
             const unsigned lower = peers & lanemask_lt();
-            uint32_t cand = L1_EMPTY;
+            uint32_t cand = CFG::EMPTY;
             if (hashable) cand = lower ? pos + (31 - __clz(lower)) : table[h];
-            const bool found = hashable && cand != L1_EMPTY && p - cand <= 32768u && ld24(in + cand) == v;
+            const bool found = hashable && cand != CFG::EMPTY && p - cand <= 32768u && ld24(in + cand) == v;
             const unsigned fb = __ballot_sync(BDF_FULL_MASK, found);
             const unsigned k = fb ? __ffs(fb) - 1 : 32;            // first lane whose probe hits
             // commit bucket writes of lanes 0..k (the match start is inserted too, :1162-1163)
             const unsigned committing = __ballot_sync(BDF_FULL_MASK, hashable && lane <= k);
             const unsigned mine = peers & committing;
-            if (hashable && lane <= k && (mine >> lane) == 1u) table[h] = (uint16_t)p;
-            // literals: lanes below k that are inside the input
+            if (hashable && lane <= k && (mine >> lane) == 1u) table[h] = (pos_t)p;
+            // this round's symbols: nl literals, then (k < 32) one match
+            const uint32_t nl = len - pos < k ? len - pos : k;
+            uint32_t mp = 0, mc = 0, mlen = 0;
+            if (k < 32) {
+                mp = pos + k;
+                mc = __shfl_sync(BDF_FULL_MASK, cand, k);
+                const unsigned room = len - mp < 258 ? len - mp : 258;
+                mlen = warp_match_len(in + mc, in + mp, room, lane);
+            }
+            // Block splitting does not touch the parse (no lazy evaluation, the table carries
+            // over), it only decides where end-of-block + a new header go into the bit stream.
+            // should_end_block can only act once 2048 observations are pending, so rounds that
+            // cannot reach that are counted in bulk; the others are replayed symbol by symbol.
+            uint32_t cut = 0xFFFFFFFFu;                 // literal index in front of which the block ends
+            if (split) {
+                const uint32_t pending = st.num_new;
+                __syncwarp();
+                if (pending + nl < 2048) {
+                    if (lane < nl) atomicAdd(&st.new_obs[in[p] >> 5], 1u);
+                    __syncwarp();
+                    if (lane == 0) {
+                        st.num_new = pending + nl;
+                        if (k < 32) {
+                            const unsigned slot = offset_slot_of(mp - mc);
+                            st.new_obs[8 + (mlen >= 8)]++;
+                            st.new_obs[10 + (slot < 16 ? 0 : slot < 24 ? 1 : slot < 30 ? 2 : 0)]++;
+                            st.num_new += 2;
+                        }
+                    }
+                } else {
+                    if (lane == 0) {
+                        for (uint32_t j = 0; j <= nl; j++) {
+                            if (j == nl && k == 32) break;      // no symbol follows in this round
+                            if (hc_should_end(st, pos + j - block_start, len - (pos + j))) {
+                                cut = j;                        // at most once per round: 2048 more are needed
+                                block_start = pos + j;
+                                for (int c = 0; c < 14; c++) { st.new_obs[c] = 0; st.obs[c] = 0; }
+                                st.num_new = 0; st.num_obs = 0;
+                            }
+                            if (j < nl) { st.new_obs[in[pos + j] >> 5]++; st.num_new++; }
+                        }
+                        if (k < 32) {
+                            const unsigned slot = offset_slot_of(mp - mc);
+                            st.new_obs[8 + (mlen >= 8)]++;
+                            st.new_obs[10 + (slot < 16 ? 0 : slot < 24 ? 1 : slot < 30 ? 2 : 0)]++;
+                            st.num_new += 2;
+                        }
+                    }
+                    cut = __shfl_sync(BDF_FULL_MASK, cut, 0);
+                    block_start = __shfl_sync(BDF_FULL_MASK, block_start, 0);
+                }
+                __syncwarp();
+            }
+            // literals: lanes below nl
             uint32_t bits = 0, nb = 0;
-            if (lane < k && p < len) static_lit_code(in[p], bits, nb);
-            bs.put(bits, nb, lane);
+            if (lane < nl) static_lit_code(in[p], bits, nb);
+            if (cut == 0xFFFFFFFFu) {
+                bs.put(bits, nb, lane);
+            } else {
+                bs.put(lane < cut ? bits : 0, lane < cut ? nb : 0, lane);
+                bs.put1(0, 7, lane);                     // end of block (symbol 256 = 0000000)
+                bfinal_at = bs.bitpos();
+                bs.put1(2u, 3, lane);                    // BFINAL = 0 for now, BTYPE = 01
+                bs.put(lane >= cut ? bits : 0, lane >= cut ? nb : 0, lane);
+            }
             if (k == 32) { pos += 32; continue; }
-            const uint32_t mp = pos + k;
-            const uint32_t mc = __shfl_sync(BDF_FULL_MASK, cand, k);
-            const unsigned room = len - mp < 258 ? len - mp : 258;
-            const unsigned mlen = warp_match_len(in + mc, in + mp, room, lane);
             uint32_t b0, n0, b1, n1;
             static_len_code(mlen, b0, n0);
             static_off_code(mp - mc, b1, n1);
@@ -118,11 +201,13 @@ __global__ void __launch_bounds__(L1_WARPS * 32) deflate_l1_kernel(DeflateArgs a
             __syncwarp();
         }
         bs.put1(0, 7, lane);                     // end of block (symbol 256 = 0000000)
+        if (split && (uflags & UNIT_FINISH)) bs.set_bit(bfinal_at, lane);
+        if (uflags & UNIT_SYNC) bs.sync_marker(lane);
         uint64_t sz = bs.finish(lane);
-        int st = BDF_OK;
-        if (sz == ~0ull) { st = BDF_INSUFFICIENT_SPACE; sz = 0; }
+        int st_code = BDF_OK;
+        if (sz == ~0ull) { st_code = BDF_INSUFFICIENT_SPACE; sz = 0; }
         else sz = frame_footer(a.format, in, len, out, hdr + sz, sm.crc, sm.x2n, lane);
-        if (lane == 0) { a.status[idx] = st; a.out_size[idx] = sz; }
+        if (lane == 0) { a.status[idx] = st_code; a.out_size[idx] = sz; }
         __syncwarp();
     }
 }

@@ -82,7 +82,7 @@ def large_inputs():
     ]
 
 
-LARGE_LEVELS = [0, 2, 6, 9]
+LARGE_LEVELS = [0, 1, 2, 6, 9]
 
 
 def test_large_streams_chunked_byte_identical(engine):
@@ -102,15 +102,15 @@ def test_large_streams_chunked_byte_identical(engine):
     assert engine.BatchDecompressor(format=2).decompress_batch(comp, [len(s) for s in ins]) == ins
 
 
-def test_large_streams_unsupported_levels_fail_loudly(engine):
-    # levels not yet built for units above 64 KiB: an error, never a silent empty result
-    big = corpus.text_stream(6, 70000)
-    for level in [l for l in range(1, 13) if l not in LARGE_LEVELS]:
-        try:
-            got = engine.BatchCompressor(level).compress_batch([big])
-        except engine.BdfError:
-            continue
-        assert got == [o.compress(big, level)], level
+def test_large_streams_near_optimal_levels(engine):
+    """Levels 10..12 above 64 KiB (one serial thread per 256 KiB unit: slow, so few and small)."""
+    ins = [corpus.text_stream(6, 70000), (corpus.binary_stream(4) * 5)[:300000], b"tiny"]
+    for level, fmt in ((10, 0), (12, 1)):
+        batch = ins if level == 10 else ins[:1] + ins[2:]
+        got = engine.BatchCompressor(level, format=fmt).compress_batch(batch)
+        for g, s in zip(got, batch):
+            assert g == o.compress(s, level, fmt), (level, len(s))
+            assert zlib.decompress(g, WBITS[fmt]) == s
 
 
 def test_compress_failure_is_in_band(engine):
