@@ -91,7 +91,8 @@ size_t bdf_compress_bound(int format, size_t len);
  *   out_size[i] : bytes produced (0 on failure); status[i] : bdf_status
  *   checksum[i] (may be NULL): Adler-32 (zlib) / CRC-32 (gzip) of the output, 0 for raw
  * Like the reference, trailing input after the final block is ignored and
- * producing fewer than max_out[i] bytes is success.
+ * producing fewer than max_out[i] bytes is success.  The *_host calls reject input and output
+ * ranges that overlap (is_overlapping, src/api.rs:303-314) with BDF_E_ARG.
  * *_device: every pointer is device memory valid on the ctx's device; the
  * work is enqueued on `stream` (a cudaStream_t; NULL means the ctx's own
  * stream — pass cudaStreamLegacy / cudaStreamPerThread explicitly to target
@@ -133,6 +134,20 @@ int bdf_compress_batch_host(bdf_ctx *ctx, int level, int format, const uint8_t *
                             const uint64_t *in_off, size_t n, uint8_t *out,
                             const uint64_t *out_off, uint64_t *out_size,
                             int32_t *status);
+
+/*
+ * Compressor::compress(chunk, out, FlushMode) for many chunks at once (src/compress/mod.rs:693-790)
+ * — the call DeflateEncoder::flush_buffer makes for every 256 KiB chunk of its buffer
+ * (src/stream.rs:42-196).  Unit i = in[unit_off[i] .. unit_off[i+1]) (at most 262144 bytes),
+ * raw DEFLATE, each through a fresh compressor; flush[i] = BDF_FLUSH_FINISH ends the stream
+ * (last block has BFINAL), BDF_FLUSH_SYNC ends the unit with a sync flush (empty stored block
+ * 00 00 FF FF, :662-681).  Room per unit: bdf_compress_bound(BDF_RAW, len), plus 5 for a sync
+ * unit, like the encoder's own buffers (src/stream.rs:66-69).
+ */
+typedef enum bdf_flush { BDF_FLUSH_SYNC = 1, BDF_FLUSH_FINISH = 2 } bdf_flush;
+int bdf_compress_units_host(bdf_ctx *ctx, int level, const uint8_t *in, const uint64_t *unit_off,
+                            const uint8_t *flush, size_t n, uint8_t *out, const uint64_t *out_off,
+                            uint64_t *out_size, int32_t *status);
 
 /* adler32(1, data) / crc32(0, data) per stream (src/adler32/mod.rs:114-152,
  * src/crc32/mod.rs:331-365). */

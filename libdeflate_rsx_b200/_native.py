@@ -12,6 +12,7 @@ SO_PATH = os.path.join(HERE, "libbdeflate.so")
 RAW, ZLIB, GZIP = 0, 1, 2
 OK, BAD_DATA, SHORT_OUTPUT, INSUFFICIENT_SPACE, SHORT_INPUT = range(5)
 ADLER32, CRC32 = 0, 1
+FLUSH_SYNC, FLUSH_FINISH = 1, 2
 E_OK, E_ARG, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4
 
 EXPORTS = [
@@ -19,7 +20,7 @@ EXPORTS = [
     "bdf_kernel_launches", "bdf_last_kernel_ms", "bdf_host_alloc", "bdf_host_free",
     "bdf_compress_bound", "bdf_decompress_batch_device", "bdf_decompress_batch_host",
     "bdf_compress_batch_device", "bdf_compress_batch_host", "bdf_checksum_batch_device",
-    "bdf_checksum_batch_host", "bdf_gather_streams_device",
+    "bdf_checksum_batch_host", "bdf_gather_streams_device", "bdf_compress_units_host",
 ]
 
 
@@ -64,6 +65,8 @@ def load():
     L.bdf_checksum_batch_device.argtypes = [vp, C.c_int, vp, vp, sz, vp, vp]
     L.bdf_checksum_batch_host.restype = C.c_int
     L.bdf_checksum_batch_host.argtypes = [vp, C.c_int, vp, vp, sz, vp]
+    L.bdf_compress_units_host.restype = C.c_int
+    L.bdf_compress_units_host.argtypes = [vp, C.c_int, vp, vp, vp, sz, vp, vp, vp, vp]
     L.bdf_gather_streams_device.restype = C.c_int
     L.bdf_gather_streams_device.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
     return L

@@ -119,6 +119,14 @@ int launch_inflate(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
 
 bool bad_format(int f) { return f != BDF_RAW && f != BDF_ZLIB && f != BDF_GZIP; }
 
+// is_overlapping, src/api.rs:303-314: the safe API rejects calls whose input and output alias
+bool overlaps(const void *a, size_t na, const void *b, size_t nb)
+{
+    const uintptr_t p1 = (uintptr_t)a, p2 = (uintptr_t)b;
+    const uintptr_t e1 = p1 + na < p1 ? UINTPTR_MAX : p1 + na, e2 = p2 + nb < p2 ? UINTPTR_MAX : p2 + nb;
+    return (p1 > p2 ? p1 : p2) < (e1 < e2 ? e1 : e2);
+}
+
 }  // namespace
 
 extern "C" {
@@ -255,6 +263,7 @@ int bdf_decompress_batch_host(bdf_ctx *ctx, int format, const uint8_t *in, const
         size_t e = (size_t)(out_off[i] + max_out[i]);
         if (e > out_bytes) out_bytes = e;
     }
+    if (overlaps(in, in_bytes, out, out_bytes)) return fail(ctx, BDF_E_ARG, "Input and output buffers overlap");
     int rc;
     if ((rc = ensure(ctx, ctx->in, in_bytes + 8)) || (rc = ensure(ctx, ctx->out, out_bytes + 8)) ||
         (rc = ensure(ctx, ctx->in_off, (n + 1) * 8)) || (rc = ensure(ctx, ctx->out_off, n * 8)) ||
@@ -401,6 +410,7 @@ int bdf_compress_batch_host(bdf_ctx *ctx, int level, int format, const uint8_t *
             size_t e = (size_t)out_off[i] + bdf_compress_bound(format, (size_t)(in_off[i + 1] - in_off[i]));
             if (e > out_bytes) out_bytes = e;
         }
+        if (overlaps(in, in_bytes, out, out_bytes)) return fail(ctx, BDF_E_ARG, "Input and output buffers overlap");
         int rc;
         if ((rc = ensure(ctx, ctx->in, in_bytes + 8)) || (rc = ensure(ctx, ctx->out, out_bytes + 8)) ||
             (rc = ensure(ctx, ctx->in_off, (n + 1) * 8)) || (rc = ensure(ctx, ctx->out_off, n * 8)) ||
@@ -446,6 +456,73 @@ int bdf_compress_batch_host(bdf_ctx *ctx, int level, int format, const uint8_t *
                                           cudaMemcpyDeviceToHost, s));
         i = j;
     }
+    CK(cudaStreamSynchronize(s));
+    return BDF_E_OK;
+}
+
+// --------------------------------------------------------------------- units
+int bdf_compress_units_host(bdf_ctx *ctx, int level, const uint8_t *in, const uint64_t *unit_off,
+                            const uint8_t *flush, size_t n, uint8_t *out, const uint64_t *out_off,
+                            uint64_t *out_size, int32_t *status)
+{
+    if (!ctx) return BDF_E_ARG;
+    if (level < 0) return fail(ctx, BDF_E_ARG, "negative level");
+    if (n == 0) return BDF_E_OK;
+    if (!in || !unit_off || !flush || !out || !out_off || !out_size || !status)
+        return fail(ctx, BDF_E_ARG, "null pointer");
+    if (n > 0xFFFFFFF0ull) return fail(ctx, BDF_E_ARG, "too many units");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    std::vector<uint8_t> uflags(n);
+    uint64_t max_unit = 0;
+    size_t out_bytes = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t ul = unit_off[i + 1] - unit_off[i];
+        if (ul > 256u * 1024u) return fail(ctx, BDF_E_ARG, "a unit is at most 262144 bytes");
+        if (flush[i] != BDF_FLUSH_SYNC && flush[i] != BDF_FLUSH_FINISH) return fail(ctx, BDF_E_ARG, "unknown flush mode");
+        // DeflateEncoder gives a chunk that ends in a sync flush 5 more bytes of room (src/stream.rs:66-69,113-116)
+        uflags[i] = flush[i] == BDF_FLUSH_FINISH ? (uint8_t)bdf::UNIT_FINISH : (uint8_t)(bdf::UNIT_SYNC | bdf::UNIT_CAP5);
+        if (ul > max_unit) max_unit = ul;
+        const size_t e = (size_t)out_off[i] + (size_t)bdf::unit_cap(ul, uflags[i]);
+        if (e > out_bytes) out_bytes = e;
+    }
+    const size_t in_bytes = (size_t)unit_off[n];
+    if (overlaps(in, in_bytes, out, out_bytes)) return fail(ctx, BDF_E_ARG, "Input and output buffers overlap");
+    int rc;
+    if ((rc = ensure(ctx, ctx->in, in_bytes + 8)) || (rc = ensure(ctx, ctx->out, out_bytes + 8)) ||
+        (rc = ensure(ctx, ctx->in_off, (n + 1) * 8)) || (rc = ensure(ctx, ctx->out_off, n * 8)) ||
+        (rc = ensure(ctx, ctx->out_size, n * 8)) || (rc = ensure(ctx, ctx->status, n * 4)) ||
+        (rc = ensure(ctx, ctx->u_flags, n)))
+        return rc;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->in.p, in, in_bytes, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->in_off.p, unit_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->out_off.p, out_off, n * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->u_flags.p, uflags.data(), n, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventRecord(ctx->ev0, s));
+    bdf::DeflateArgs a;
+    a.in = (const uint8_t *)ctx->in.p; a.in_off = (const uint64_t *)ctx->in_off.p;
+    a.out = (uint8_t *)ctx->out.p; a.out_off = (const uint64_t *)ctx->out_off.p;
+    a.out_size = (uint64_t *)ctx->out_size.p; a.status = (int32_t *)ctx->status.p;
+    a.n = (uint32_t)n; a.level = level > 12 ? 12 : level; a.format = BDF_RAW;
+    a.unit_flags = (const uint8_t *)ctx->u_flags.p;
+    a.work_counter = next_counter(ctx, s);
+    int nl = 0;
+    const char *why = nullptr;
+    cudaError_t e = bdf::launch_deflate(a, ctx->deflate_scratch, ctx->sm_count, s, &nl, &why, max_unit);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail(ctx, BDF_E_CUDA, why ? why : "launch_deflate", e);
+    if (why) return fail(ctx, BDF_E_UNSUPPORTED, why);
+    CK(cudaEventRecord(ctx->ev1, s));
+    CK(cudaMemcpyAsync(out_size, ctx->out_size.p, n * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(status, ctx->status.p, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    for (size_t i = 0; i < n; i++)
+        if (out_size[i])
+            CK(cudaMemcpyAsync(out + out_off[i], (const uint8_t *)ctx->out.p + out_off[i], (size_t)out_size[i],
+                               cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return BDF_E_OK;
 }

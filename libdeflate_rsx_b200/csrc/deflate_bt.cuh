@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(BT_THREADS) deflate_bt_kernel(DeflateArgs a)
             hdr = 10;
         }
         ThreadBits bs;
-        bs.out = out + hdr; bs.cap = deflate_bound(len); bs.pos = 0; bs.buf = 0; bs.cnt = 0; bs.overflow = false;
+        bs.out = out + hdr; bs.cap = unit_cap(len, uflags); bs.pos = 0; bs.buf = 0; bs.cnt = 0; bs.overflow = false;
         bt_reset(bt);
         uint32_t p = 0;
         do {

@@ -27,7 +27,8 @@ struct DeflateArgs {
     // entry is a whole stream (finish, no sync).
     const uint8_t *unit_flags;
 };
-constexpr unsigned UNIT_FINISH = 1u, UNIT_SYNC = 2u;
+constexpr unsigned UNIT_FINISH = 1u, UNIT_SYNC = 2u, UNIT_CAP5 = 4u;   // CAP5: 5 more bytes of room (DeflateEncoder, src/stream.rs:66-69)
+__host__ __device__ inline uint64_t unit_cap(uint64_t len, unsigned flags) { return len + (len / 65535 + 1) * 5 + 10 + ((flags & 4u) ? 5 : 0); }
 __device__ __forceinline__ unsigned unit_flags_of(const DeflateArgs &a, uint64_t idx)
 {
     return a.unit_flags ? a.unit_flags[idx] : UNIT_FINISH;

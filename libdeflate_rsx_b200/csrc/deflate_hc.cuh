@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(HC_THREADS) deflate_hc_kernel(DeflateArgs a)
         BitSink bs;
         if (warp == 0) {
             hdr = frame_header(a.format, a.level, out, lane);
-            bs.init(sm.sink, out + hdr, deflate_bound(len), lane);
+            bs.init(sm.sink, out + hdr, unit_cap(len, uflags), lane);
         }
         __syncthreads();
 

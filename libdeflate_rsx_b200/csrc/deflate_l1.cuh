@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(L1_WARPS * 32) deflate_l1_kernel(DeflateArgs a
         for (unsigned i = lane; i < CFG::TABLE_BYTES / 16; i += 32) reinterpret_cast<uint4 *>(table)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
         const unsigned hdr = frame_header(a.format, 1, out, lane);
         BitSink bs;
-        bs.init(sm.sink[warp], out + hdr, deflate_bound(len), lane);
+        bs.init(sm.sink[warp], out + hdr, unit_cap(len, uflags), lane);
         // BTYPE = 01; BFINAL of a block that may still be split is written as 0 and set at the end
         uint64_t bfinal_at = bs.bitpos();
         bs.put1((!split && (uflags & UNIT_FINISH) ? 1u : 0u) | 2u, 3, lane);

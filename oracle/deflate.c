@@ -908,6 +908,19 @@ static int compress_raw(int level, const uint8_t *in, size_t n, uint8_t *out, si
     return ORC_OK;
 }
 
+int orc_compress_unit(int level, const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap,
+                      int finish, int sync, size_t *out_size)
+{
+    if (!__atomic_load_n(&tabs_ready, __ATOMIC_ACQUIRE))
+        init_tabs();
+    *out_size = 0;
+    if (level < 0)
+        level = 0;
+    if (in_len > 256 * 1024)
+        return ORC_BAD_DATA;
+    return compress_one(level, in, in_len, out, out_cap, finish, sync, out_size);
+}
+
 int orc_compress(int level, int format, const uint8_t *in, size_t in_len, uint8_t *out,
                  size_t out_cap, size_t *out_size)
 {

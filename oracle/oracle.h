@@ -53,6 +53,12 @@ size_t orc_compress_bound(int format, size_t len);
 int orc_compress(int level, int format, const uint8_t *in, size_t in_len,
                  uint8_t *out, size_t out_cap, size_t *out_size);
 
+/* Compressor::compress(chunk, out, FlushMode), src/compress/mod.rs:693-790, for one chunk of at
+ * most 256 KiB: raw DEFLATE; finish = FlushMode::Finish, sync = FlushMode::Sync (:662-681).
+ * This is what DeflateEncoder::flush_buffer calls per chunk (src/stream.rs:42-196). */
+int orc_compress_unit(int level, const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap,
+                      int finish, int sync, size_t *out_size);
+
 /* One stream.  in_consumed follows the reference (reader position, see
  * inflate.c header).  Returns an ORC_* status. */
 int orc_decompress(int format, const uint8_t *in, size_t in_len, uint8_t *out,

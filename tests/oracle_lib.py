@@ -41,6 +41,9 @@ def lib():
         L.orc_compress.restype = C.c_int
         L.orc_compress.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_size_t,
                                    C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.orc_compress_unit.restype = C.c_int
+        L.orc_compress_unit.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                        C.c_int, C.c_int, C.POINTER(C.c_size_t)]
         L.orc_decompress.restype = C.c_int
         L.orc_decompress.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                      C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
@@ -77,6 +80,16 @@ def compress(data, level, fmt=RAW, cap=None):
     out = C.create_string_buffer(max(cap, 1))
     sz = C.c_size_t(0)
     st = lib().orc_compress(level, fmt, data, len(data), out, cap, C.byref(sz))
+    return out.raw[:sz.value] if st == OK else None
+
+
+def compress_unit(data, level, finish, sync, cap=None):
+    """Compressor::compress(chunk, out, mode) for one chunk (<= 256 KiB); None on InsufficientSpace."""
+    data = bytes(data)
+    cap = compress_bound(RAW, len(data)) + (5 if sync else 0) if cap is None else cap
+    out = C.create_string_buffer(max(cap, 1))
+    sz = C.c_size_t(0)
+    st = lib().orc_compress_unit(level, data, len(data), out, cap, int(finish), int(sync), C.byref(sz))
     return out.raw[:sz.value] if st == OK else None
 
 

@@ -59,3 +59,24 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_lib" not in text and "liboracle" not in text and "orc_" not in text, f
+
+
+def test_safe_api_guards_need_no_gpu():
+    """src/api.rs host logic: level validation (:10-16), zip-bomb guards (:213-239), bounds (:59-69)."""
+    import pytest
+    import libdeflate_rsx_b200 as bdf
+    for bad in (-1, 13):
+        with pytest.raises(ValueError, match="between 0 and 12"):
+            bdf.Compressor(bad)
+    c = bdf.Compressor(6)
+    assert c.deflate_compress_bound(65536) == 65536 + 2 * 5 + 10
+    assert c.zlib_compress_bound(0) == 5 + 10 + 6 and c.gzip_compress_bound(0) == 5 + 10 + 18
+    d = bdf.Decompressor()
+    with pytest.raises(ValueError, match="safety limit"):
+        d.decompress_deflate(bytes(10), 30000)              # 30000 > 10 * 2000 + 4096
+    d.set_max_memory_limit(50 << 20)
+    with pytest.raises(ValueError, match="maximum memory limit"):
+        d.decompress_zlib(bytes(1 << 20), 100 << 20)
+    d.set_limit_ratio(10)
+    with pytest.raises(ValueError, match="safety limit"):
+        d.decompress_gzip_batch([bytes(10), bytes(10)], [4000, 5000])   # second stream: 5000 > 4196
