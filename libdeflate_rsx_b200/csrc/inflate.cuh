@@ -31,10 +31,14 @@ constexpr int LT_BITS = 9;    // litlen direct-table bits
 constexpr int OT_BITS = 7;    // offset direct-table bits (the precode table, 7 bits, overlays it)
 constexpr int PT_BITS = 7;    // precode direct-table bits
 
-// Table entry (u32): [4:0] codeword bits (0 = longer than the table),
-// [8:5] extra bits, [10:9] kind, [15] literal, [31:16] literal / base value.
-constexpr uint32_t K_LIT = 0u << 9, K_BASE = 1u << 9, K_EOB = 2u << 9, K_MASK = 3u << 9;
-constexpr uint32_t LITFLAG = 1u << 15;    // set in literal entries only: one test selects the literal fast path
+// Table entry (u16 — 32-bit entries cost 1.3 KiB more shared memory per stream, i.e. two CTAs per
+// SM): [3:0] codeword bits (0 = longer than the table), [5:4] kind, [6] literal,
+// [15:7] literal byte / length slot / offset slot / precode symbol.  Base value and extra-bit
+// count of a length or offset slot are computed where a match is decoded.
+constexpr uint32_t K_LIT = 0u << 4, K_BASE = 1u << 4, K_EOB = 2u << 4, K_MASK = 3u << 4;
+constexpr uint32_t LITFLAG = 1u << 6;     // set in literal entries only: one test selects the literal fast path
+constexpr uint32_t E_LEN = 15u;           // mask of the codeword length
+constexpr int E_VAL = 7;                  // shift of the value
 
 struct HuffCode {            // canonical description used for build + long codes
     uint16_t first[16];      // first codeword of each length (MSB-first value)
@@ -57,8 +61,8 @@ struct BuildScratch {
 
 template <int G>
 struct __align__(16) InflateSmem {     // one per lane group
-    uint32_t lit_tab[1 << LT_BITS];
-    uint32_t off_tab[1 << OT_BITS];
+    uint16_t lit_tab[1 << LT_BITS];
+    uint16_t off_tab[1 << OT_BITS];
     uint16_t lit_sorted[288];
     uint16_t off_sorted[32];
     HuffCode lit_code, off_code;
@@ -138,19 +142,25 @@ struct BitReader {
 // ------------------------------------------------------------ table building
 __device__ __forceinline__ uint32_t make_litlen_entry(unsigned sym, unsigned l)
 {
-    if (sym < 256) return (sym << 16) | LITFLAG | K_LIT | l;
+    if (sym < 256) return (sym << E_VAL) | LITFLAG | K_LIT | l;
     if (sym == 256) return K_EOB | l;
-    unsigned base, extra;
-    length_slot_info(sym - 257, base, extra);
-    return (base << 16) | K_BASE | (extra << 5) | l;
+    return ((sym - 257) << E_VAL) | K_BASE | l;         // slots 29 / 30 (symbols 286 / 287) decode as 258
 }
-__device__ __forceinline__ uint32_t make_offset_entry(unsigned sym, unsigned l)
+__device__ __forceinline__ uint32_t make_offset_entry(unsigned sym, unsigned l) { return (sym << E_VAL) | K_BASE | l; }
+__device__ __forceinline__ uint32_t make_precode_entry(unsigned sym, unsigned l) { return (sym << E_VAL) | l; }
+// match length / offset of a decoded slot entry: base + the extra bits that follow the codeword
+__device__ __forceinline__ unsigned take_length(BitReader &br, uint32_t e)
 {
     unsigned base, extra;
-    offset_slot_info(sym, base, extra);
-    return (base << 16) | K_BASE | (extra << 5) | l;
+    length_slot_info(e >> E_VAL, base, extra);
+    return base + br.take(extra);
 }
-__device__ __forceinline__ uint32_t make_precode_entry(unsigned sym, unsigned l) { return (sym << 16) | l; }
+__device__ __forceinline__ unsigned take_offset(BitReader &br, uint32_t f)
+{
+    unsigned base, extra;
+    offset_slot_info(f >> E_VAL, base, extra);
+    return base + br.take(extra);
+}
 
 enum { CODE_LITLEN = 0, CODE_OFFSET = 1, CODE_PRECODE = 2 };
 
@@ -174,7 +184,7 @@ __device__ __forceinline__ uint32_t make_entry(unsigned sym, unsigned l)
 // lane walks its symbols again; rank -> codeword -> the symbol writes its own table slots.  No
 // group synchronisation inside either pass.
 template <int KIND, int TBITS, int G>
-__device__ bool build_code(const Grp<G> &g, const uint8_t *lens, unsigned nsyms, uint32_t *tab,
+__device__ bool build_code(const Grp<G> &g, const uint8_t *lens, unsigned nsyms, uint16_t *tab,
                            uint16_t *sorted, HuffCode &hc, BuildScratch<G> &bs)
 {
     static_assert(G >= 16, "one length owner per code length");
@@ -230,7 +240,7 @@ __device__ bool build_code(const Grp<G> &g, const uint8_t *lens, unsigned nsyms,
             }
         }
         const uint32_t e = make_entry<KIND>(sym, 1);
-        for (unsigned i = g.lane; i < (1u << TBITS); i += G) tab[i] = e;
+        for (unsigned i = g.lane; i < (1u << TBITS); i += G) tab[i] = (uint16_t)e;
         for (unsigned i = g.lane; i < 16; i += G) hc.count[i] = 0;   // no long codes
         g.sync();
         return true;
@@ -251,7 +261,7 @@ __device__ bool build_code(const Grp<G> &g, const uint8_t *lens, unsigned nsyms,
                 bs.big_e[k] = e;
                 bs.big_r[k] = (uint16_t)(rev | l << 12);
             } else {
-                for (unsigned i = rev; i < (1u << TBITS); i += 1u << l) tab[i] = e;
+                for (unsigned i = rev; i < (1u << TBITS); i += 1u << l) tab[i] = (uint16_t)e;
             }
         } else {
             tab[rev & ((1u << TBITS) - 1u)] = 0;
@@ -262,7 +272,7 @@ __device__ bool build_code(const Grp<G> &g, const uint8_t *lens, unsigned nsyms,
     for (unsigned k = 0; k < nbig; k++) {
         const uint32_t e = bs.big_e[k];
         const unsigned r = bs.big_r[k], l = r >> 12;
-        for (unsigned i = (r & 0xFFFu) + (g.lane << l); i < (1u << TBITS); i += (unsigned)G << l) tab[i] = e;
+        for (unsigned i = (r & 0xFFFu) + (g.lane << l); i < (1u << TBITS); i += (unsigned)G << l) tab[i] = (uint16_t)e;
     }
     g.sync();
     return true;
@@ -682,8 +692,8 @@ __device__ __forceinline__ int decode_step(const Grp<G> &g, BitReader &br, OutSt
 #define BDF_PARK_LITERAL(e)                                                          \
     do {                                                                             \
         if (o.pos + o.npend >= o.cap) return BDF_INSUFFICIENT_SPACE;                 \
-        br.drop((e) & 31u);                                                          \
-        if (g.lane == o.npend) o.mylit = (e) >> 16;                                  \
+        br.drop((e) & E_LEN);                                                        \
+        if (g.lane == o.npend) o.mylit = (e) >> E_VAL;                               \
         if (++o.npend == G) {                                                        \
             make_valid<G>(g, o, o.pos + 2 * G);                                      \
             flush_literals<ADLER>(o, g.lane);                                        \
@@ -710,7 +720,7 @@ __device__ __forceinline__ int decode_step(const Grp<G> &g, BitReader &br, OutSt
         const uint32_t tok_lo = (uint32_t)br.buf;      // >= 33 valid bits: the next 32 bits of the stream
         const int32_t tok_left = br.left;
         const uint32_t tok_widx = br.widx;
-        if ((e & 31u) == 0) {
+        if ((e & E_LEN) == 0) {
             e = decode_long<CODE_LITLEN, LT_BITS>(br.peek(15), sm.lit_sorted, sm.lit_code);
             if (e == 0) return BDF_BAD_DATA;
         }
@@ -719,19 +729,19 @@ __device__ __forceinline__ int decode_step(const Grp<G> &g, BitReader &br, OutSt
             BDF_PARK_LITERAL(e);
             return STEP_MORE;
         }
-        br.drop(e & 31u);
+        br.drop(e & E_LEN);
         if (kind == K_EOB) {
             return br.overrun() ? BDF_SHORT_INPUT : BDF_OK;
         }
-        unsigned length = (e >> 16) + br.take((e >> 5) & 15u);
+        unsigned length = take_length(br, e);
         br.refill();                                   // appends above `left`: consumed-bit accounting is unchanged
         uint32_t f = sm.off_tab[br.peek(OT_BITS)];
-        if ((f & 31u) == 0) {
+        if ((f & E_LEN) == 0) {
             f = decode_long<CODE_OFFSET, OT_BITS>(br.peek(15), sm.off_sorted, sm.off_code);
             if (f == 0) return BDF_BAD_DATA;
         }
-        br.drop(f & 31u);
-        const unsigned offset = (f >> 16) + br.take((f >> 5) & 15u);
+        br.drop(f & E_LEN);
+        const unsigned offset = take_offset(br, f);
         flush_literals<ADLER>(o, g.lane);
         if (offset > o.pos) return BDF_BAD_DATA;
         if (o.pos + length > o.cap) return BDF_INSUFFICIENT_SPACE;
@@ -779,16 +789,16 @@ __device__ __forceinline__ int decode_step(const Grp<G> &g, BitReader &br, OutSt
                 if (t.widx > t.nwords + 2) break;
                 t.refill();
                 uint32_t e2 = sm.lit_tab[t.peek(LT_BITS)];
-                if ((e2 & 31u) == 0) e2 = decode_long<CODE_LITLEN, LT_BITS>(t.peek(15), sm.lit_sorted, sm.lit_code);
-                if ((e2 & 31u) == 0 || (e2 & K_MASK) != K_BASE) break;
-                t.drop(e2 & 31u);
-                const unsigned len2 = (e2 >> 16) + t.take((e2 >> 5) & 15u);
+                if ((e2 & E_LEN) == 0) e2 = decode_long<CODE_LITLEN, LT_BITS>(t.peek(15), sm.lit_sorted, sm.lit_code);
+                if ((e2 & E_LEN) == 0 || (e2 & K_MASK) != K_BASE) break;
+                t.drop(e2 & E_LEN);
+                const unsigned len2 = take_length(t, e2);
                 t.refill();
                 uint32_t f2 = sm.off_tab[t.peek(OT_BITS)];
-                if ((f2 & 31u) == 0) f2 = decode_long<CODE_OFFSET, OT_BITS>(t.peek(15), sm.off_sorted, sm.off_code);
-                if ((f2 & 31u) == 0) break;
-                t.drop(f2 & 31u);
-                const unsigned off2 = (f2 >> 16) + t.take((f2 >> 5) & 15u);
+                if ((f2 & E_LEN) == 0) f2 = decode_long<CODE_OFFSET, OT_BITS>(t.peek(15), sm.off_sorted, sm.off_code);
+                if ((f2 & E_LEN) == 0) break;
+                t.drop(f2 & E_LEN);
+                const unsigned off2 = take_offset(t, f2);
                 if (off2 != offset || length + len2 > COALESCE_MAX || o.pos + length + len2 > o.cap) break;
                 br = t;
                 length += len2;
@@ -831,7 +841,7 @@ __device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, InflateSmem<G
         g.sync();
     }
     if (br.overrun()) return BDF_SHORT_INPUT;
-    uint32_t *pre_tab = sm.off_tab;
+    uint16_t *pre_tab = sm.off_tab;
     if (!build_code<CODE_PRECODE, PT_BITS, G>(g, pre_lens, 19, pre_tab, sm.off_sorted, sm.off_code, sm.bs))
         return BDF_BAD_DATA;
     // run-length decode of the litlen + offset code lengths (group-uniform)
@@ -844,17 +854,17 @@ __device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, InflateSmem<G
         uint32_t e = pre_tab[br.peek(PT_BITS)];
         unsigned k = 0;
         bool again = false;
-        while ((e >> 16) < 16) {
-            if (g.lane == 0) sm.lens[i] = (uint8_t)(e >> 16);
-            prev = e >> 16;
-            br.drop(e & 31u);
+        while ((e >> E_VAL) < 16) {
+            if (g.lane == 0) sm.lens[i] = (uint8_t)(e >> E_VAL);
+            prev = e >> E_VAL;
+            br.drop(e & E_LEN);
             i++;
             if (++k == 3 || i >= total) { again = true; break; }
             e = pre_tab[br.peek(PT_BITS)];
         }
         if (again) continue;
-        br.drop(e & 31u);
-        const unsigned sym = e >> 16;
+        br.drop(e & E_LEN);
+        const unsigned sym = e >> E_VAL;
         unsigned rep, val;
         if (sym == 16) {
             if (i == 0) return BDF_BAD_DATA;
@@ -1042,7 +1052,7 @@ struct InflateArgs {
 constexpr int INF_THREADS = 64;     // threads per CTA; 64 / G lane groups = streams in flight per CTA
 
 template <int FORMAT, int G>
-__global__ void __launch_bounds__(INF_THREADS, 12)
+__global__ void __launch_bounds__(INF_THREADS, 14)
 inflate_kernel(InflateArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
