@@ -540,6 +540,9 @@ __device__ __forceinline__ void copy_match_part(const Grp<G> &g, OutState &o, un
 constexpr uint32_t COPY_PART = 4096;
 constexpr uint32_t LONG_D_MAX = 4096;
 constexpr uint32_t LONG_MIN_BODY = 512;
+#ifndef BDF_TMA_REPLAY
+#define BDF_TMA_REPLAY 1
+#endif
 constexpr uint32_t SMEM_BLOCK_MAX = 1024;        // bytes of BuildScratch + lens usable as a block buffer
 
 // bytes [0, n) of w (n may be <= 0 or >= 4)
@@ -637,14 +640,51 @@ __device__ __forceinline__ void copy_match(const Grp<G> &g, OutState &o, unsigne
         const uint32_t q = n2 / dist, r = n2 - q * dist;
         uint32_t SD = 0, WD = 0, SR = 0, WR = 0;
         if (dist <= SMEM_BLOCK_MAX) {
-            // small blocks are staged in shared memory (the table builder's scratch is idle while
-            // symbols are decoded): no L1 tags, no misses, ~25 cycles per load
+            // Small blocks are staged in shared memory (the table builder's scratch is idle while
+            // symbols are decoded), repeated until the buffer is full, and then written by the TMA
+            // unit: one lane issues cp.async.bulk shared -> global copies of the whole buffer
+            // (UBLKCP), so the 64 KiB of a config-2 stream cost ~80 issue slots instead of 4096
+            // LDS/STG pairs and no load-to-store latency sits on the warp.  The block sums for
+            // Adler-32 are taken from the same buffer while the copies are in flight.
             uint4 *sb = reinterpret_cast<uint4 *>(ext);
-            for (uint32_t k = g.lane; k < nblk; k += G) sb[k] = blk[k];
+            const uint32_t rch = (SMEM_BLOCK_MAX / dist) * nblk;          // chunks in the repeated buffer (<= 64)
+            {
+                uint32_t j = g.lane % nblk;
+                const uint32_t gs = (uint32_t)G % nblk;
+                for (uint32_t k = g.lane; k < rch; k += G) {
+                    sb[k] = blk[j];
+                    j += gs;
+                    if (j >= nblk) j -= nblk;
+                }
+            }
+#if BDF_TMA_REPLAY
+            // the generic-proxy writes above (and the zero-fill / lead-in stores to the output) come
+            // before the async-proxy accesses below
+            asm volatile("fence.proxy.async;" ::: "memory");
             g.sync();
-            replay_block<G>(g, sb, d16, nch, nblk);
+            if (g.lane == 0) {
+                const uint32_t rbytes = rch * 16u, total = nch * 16u;
+                const uint32_t src = (uint32_t)__cvta_generic_to_shared(sb);
+                uint8_t *dst = o.out + p2;
+                uint32_t off = 0;
+                for (; off + rbytes <= total; off += rbytes)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(dst + off), "r"(src), "r"(rbytes) : "memory");
+                if (off < total)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(dst + off), "r"(src), "r"(total - off) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (ADLER) block_sums<G>(g, sb, nblk, r, SD, WD, SR, WR);
+            // complete (not only read) before anyone continues: a later match may copy from these bytes
+            if (g.lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            g.sync();
+#else
+            g.sync();
+            replay_block<G>(g, sb, d16, nch, rch);
             if (ADLER) block_sums<G>(g, sb, nblk, r, SD, WD, SR, WR);
             g.sync();                                 // ext is reused by the next match
+#endif
         } else {
             replay_block<G>(g, blk, d16, nch, nblk);
             if (ADLER) block_sums<G>(g, blk, nblk, r, SD, WD, SR, WR);
