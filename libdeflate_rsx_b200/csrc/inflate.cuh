@@ -126,6 +126,17 @@ struct BitReader {
         return (int64_t)widx * 32 - 8 * (int64_t)mis - left;
     }
     __device__ __forceinline__ bool overrun() const { return consumed_bits() > (int64_t)len * 8; }
+    // restart at bit `bit` of the stream (consumed_bits() == bit afterwards)
+    __device__ __forceinline__ void seek_bits(int64_t bit)
+    {
+        const uint64_t a = 8ull * mis + (uint64_t)bit;
+        widx = (uint32_t)(a >> 5);
+        const uint32_t sh = (uint32_t)a & 31u;
+        buf = (uint64_t)load_word(widx) >> sh;
+        left = 32 - (int32_t)sh;
+        widx++;
+        ahead = load_word(widx);
+    }
     // restart at byte offset `at` from the stream start
     __device__ __forceinline__ void seek(uint32_t at)
     {
@@ -795,6 +806,39 @@ __device__ __forceinline__ int decode_step(const Grp<G> &g, BitReader &br, OutSt
                 const uint32_t tmask = 0xFFFFFFFFu >> (32u - tok_bits);
                 const uint32_t tpat = tok_lo & tmask;
                 const unsigned len1 = length;
+                // Long runs: the G lanes check one input word each against the periodic bit
+                // pattern (the token repeated, shifted to the word's phase), a ballot gives the
+                // number of words that continue the run, and the reader jumps over all whole
+                // tokens at once — G words per round instead of one refill per 32 bits, each of
+                // which used to wait for its prefetched word.
+                {
+                    uint64_t rep64 = tpat;
+                    for (uint32_t b = tok_bits; b < 64u; b += tok_bits) rep64 |= (uint64_t)tpat << b;
+                    const uint32_t *wbase = reinterpret_cast<const uint32_t *>(br.p - br.mis);
+#pragma unroll 1
+                    for (;;) {
+                        const uint32_t have = (uint32_t)br.left;           // bits in buf: they continue the pattern too
+                        const uint64_t hmask = have >= 64u ? ~0ull : ((1ull << have) - 1ull);
+                        if ((br.buf ^ rep64) & hmask) break;
+                        const uint32_t w = br.widx + g.lane;
+                        const bool interior = w - 1u < br.nwords - 2u;     // words that lie wholly inside the stream
+                        const uint32_t word = interior ? __ldg(wbase + w) : 0u;
+                        const uint32_t q = have + 32u * g.lane;            // bit offset of the word from the token boundary
+                        const uint32_t phi = q % tok_bits;
+                        const bool ok = interior && word == (uint32_t)(rep64 >> phi);
+                        const unsigned bad = g.ballot(!ok);
+                        const uint32_t m = bad ? (uint32_t)__ffs(bad) - 1u : (uint32_t)G;
+                        uint32_t tokens = (have + 32u * m) / tok_bits;
+                        const uint32_t lim = o.cap - o.pos < COALESCE_MAX ? o.cap - o.pos : COALESCE_MAX;
+                        const uint32_t max_tok = (lim - length) / len1;    // o.pos + length <= cap was checked
+                        const bool capped = tokens >= max_tok;
+                        if (capped) tokens = max_tok;
+                        if (tokens == 0) break;
+                        length += tokens * len1;
+                        br.seek_bits(br.consumed_bits() + (int64_t)tokens * tok_bits);
+                        if (m < (uint32_t)G || capped) break;
+                    }
+                }
                 // several tokens per compare while they fit into the 32 bits a refill guarantees
                 const uint32_t nrep = 32u / tok_bits;
                 if (nrep >= 2) {
