@@ -70,6 +70,11 @@ struct __align__(16) InflateSmem {     // one per lane group
     uint8_t lens[320 + 8];
 };
 
+// Block buffer of copy_match (see there): the builder scratch + lens, or everything from
+// lit_sorted on when the block has no long codewords.  Both end at the end of lens.
+template <int G> constexpr uint32_t BLOCK_BUF_SCRATCH = (uint32_t)(offsetof(InflateSmem<G>, lens) + 328 - offsetof(InflateSmem<G>, bs)) & ~15u;
+template <int G> constexpr uint32_t BLOCK_BUF_ALL = (uint32_t)(offsetof(InflateSmem<G>, lens) + 328 - offsetof(InflateSmem<G>, lit_sorted)) & ~15u;
+
 // ------------------------------------------------------------------ bit reader
 // Group-uniform LSB-first reader over [p, p+len) using aligned 32-bit loads.
 struct BitReader {
@@ -196,7 +201,7 @@ __device__ __forceinline__ uint32_t make_entry(unsigned sym, unsigned l)
 // group synchronisation inside either pass.
 template <int KIND, int TBITS, int G>
 __device__ bool build_code(const Grp<G> &g, const uint8_t *lens, unsigned nsyms, uint16_t *tab,
-                           uint16_t *sorted, HuffCode &hc, BuildScratch<G> &bs)
+                           uint16_t *sorted, HuffCode &hc, BuildScratch<G> &bs, uint32_t *nlong = nullptr)
 {
     static_assert(G >= 16, "one length owner per code length");
     constexpr unsigned BIG = TBITS >= 5 ? TBITS - 5 : 0;      // codewords of <= BIG bits fill >= 32 slots
@@ -232,6 +237,7 @@ __device__ bool build_code(const Grp<G> &g, const uint8_t *lens, unsigned nsyms,
         if (g.lane >= (unsigned)d) { iv += x; ic += y; }
     }
     const uint32_t used = g.shfl(iv, 15), total = g.shfl(ic, 15), c1 = g.shfl(tot, 1);
+    if (nlong) *nlong = total - g.shfl(ic, TBITS);       // codewords longer than the direct table
     if (owner) {
         hc.first[L] = (uint16_t)((iv - v) >> (15 - L));
         hc.count[L] = (uint16_t)tot;
@@ -313,6 +319,7 @@ struct OutState {
     uint32_t next_fold;    // output position at which the sums are folded mod 65521
     uint32_t zfill;        // output sectors below this offset are fully valid in L2 (see make_valid)
     uint32_t zlimit;       // last offset up to which whole 32-byte sectors belong to this stream
+    uint32_t blkcap;       // bytes of shared memory copy_match may use as its block buffer (see InflateSmem)
 };
 
 // Reading a sector of which only some bytes have been written makes L2 fetch the
@@ -554,7 +561,6 @@ constexpr uint32_t LONG_MIN_BODY = 512;
 #ifndef BDF_TMA_REPLAY
 #define BDF_TMA_REPLAY 1
 #endif
-constexpr uint32_t SMEM_BLOCK_MAX = 1024;        // bytes of BuildScratch + lens usable as a block buffer
 
 // bytes [0, n) of w (n may be <= 0 or >= 4)
 __device__ __forceinline__ uint32_t keep_low_bytes(uint32_t w, int n)
@@ -650,7 +656,7 @@ __device__ __forceinline__ void copy_match(const Grp<G> &g, OutState &o, unsigne
         const uint4 *blk = reinterpret_cast<const uint4 *>(o.out + p2 - dist);
         const uint32_t q = n2 / dist, r = n2 - q * dist;
         uint32_t SD = 0, WD = 0, SR = 0, WR = 0;
-        if (dist <= SMEM_BLOCK_MAX) {
+        if (dist <= o.blkcap) {
             // Small blocks are staged in shared memory (the table builder's scratch is idle while
             // symbols are decoded), repeated until the buffer is full, and then written by the TMA
             // unit: one lane issues cp.async.bulk shared -> global copies of the whole buffer
@@ -658,7 +664,7 @@ __device__ __forceinline__ void copy_match(const Grp<G> &g, OutState &o, unsigne
             // LDS/STG pairs and no load-to-store latency sits on the warp.  The block sums for
             // Adler-32 are taken from the same buffer while the copies are in flight.
             uint4 *sb = reinterpret_cast<uint4 *>(ext);
-            const uint32_t rch = (SMEM_BLOCK_MAX / dist) * nblk;          // chunks in the repeated buffer (<= 64)
+            const uint32_t rch = (o.blkcap / dist) * nblk;                // chunks in the repeated buffer
             {
                 uint32_t j = g.lane % nblk;
                 const uint32_t gs = (uint32_t)G % nblk;
@@ -888,7 +894,8 @@ __device__ __forceinline__ int decode_step(const Grp<G> &g, BitReader &br, OutSt
                 length += len2;
             }
         }
-        copy_match<ADLER, G>(g, o, length, offset, reinterpret_cast<uint8_t *>(&sm.bs));
+        copy_match<ADLER, G>(g, o, length, offset,
+                             reinterpret_cast<uint8_t *>(o.blkcap == BLOCK_BUF_ALL<G> ? (void *)sm.lit_sorted : (void *)&sm.bs));
         if (ADLER) adler_fold(o);
     }
     return STEP_MORE;
@@ -897,8 +904,9 @@ __device__ __forceinline__ int decode_step(const Grp<G> &g, BitReader &br, OutSt
 
 // read_dynamic_huffman_header, src/decompress/mod.rs:403-507
 template <int G>
-__device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, InflateSmem<G> &sm)
+__device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, InflateSmem<G> &sm, uint32_t &nlong)
 {
+    nlong = 1;
     br.refill();
     const unsigned nlit = 257 + br.take(5);
     const unsigned noff = 1 + br.take(5);
@@ -968,10 +976,12 @@ __device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, InflateSmem<G
     }
     if (br.overrun()) return BDF_SHORT_INPUT;
     g.sync();
-    if (!build_code<CODE_OFFSET, OT_BITS, G>(g, sm.lens + nlit, noff, sm.off_tab, sm.off_sorted, sm.off_code, sm.bs))
+    uint32_t long_off = 0, long_lit = 0;
+    if (!build_code<CODE_OFFSET, OT_BITS, G>(g, sm.lens + nlit, noff, sm.off_tab, sm.off_sorted, sm.off_code, sm.bs, &long_off))
         return BDF_BAD_DATA;
-    if (!build_code<CODE_LITLEN, LT_BITS, G>(g, sm.lens, nlit, sm.lit_tab, sm.lit_sorted, sm.lit_code, sm.bs))
+    if (!build_code<CODE_LITLEN, LT_BITS, G>(g, sm.lens, nlit, sm.lit_tab, sm.lit_sorted, sm.lit_code, sm.bs, &long_lit))
         return BDF_BAD_DATA;
+    nlong = long_off + long_lit;
     return BDF_OK;
 }
 
@@ -1038,12 +1048,17 @@ __device__ int inflate_stream(const Grp<G> &g, const uint8_t *p, uint32_t len, O
                 st = BDF_BAD_DATA;
                 live = false;
             } else {
+                uint32_t nlong = 0;                    // the static codes fit the direct tables
                 if (type == 1) {
                     load_static_codes<G>(g, sm);
                 } else {
-                    st = read_dynamic_header<G>(g, br, sm);
+                    st = read_dynamic_header<G>(g, br, sm, nlong);
                     if (st != BDF_OK) live = false;
                 }
+                // A block without codewords longer than the direct tables never looks at the sorted
+                // symbol lists / first-code arrays again: copy_match may use them, together with the
+                // builder scratch, as its block buffer (bigger TMA copies).
+                o.blkcap = nlong == 0 ? BLOCK_BUF_ALL<G> : BLOCK_BUF_SCRATCH<G>;
                 g.sync();
                 inblock = live;
             }
@@ -1143,9 +1158,10 @@ inflate_kernel(InflateArgs a)
     __shared__ uint32_t s_crc[FORMAT == BDF_GZIP ? 4 : 1][256];
     __shared__ uint32_t s_x2n[32];
     InflateSmem<G> &sm = reinterpret_cast<InflateSmem<G> *>(smem_raw)[threadIdx.x / G];
-    static_assert(offsetof(InflateSmem<G>, bs) % 16 == 0 && sizeof(InflateSmem<G>) % 16 == 0 &&
-                      offsetof(InflateSmem<G>, lens) + sizeof(sm.lens) - offsetof(InflateSmem<G>, bs) >= SMEM_BLOCK_MAX,
-                  "builder scratch + lens double as the 16-byte aligned block buffer of copy_match");
+    static_assert(offsetof(InflateSmem<G>, bs) % 16 == 0 && offsetof(InflateSmem<G>, lit_sorted) % 16 == 0 &&
+                      sizeof(InflateSmem<G>) % 16 == 0 && BLOCK_BUF_SCRATCH<G> >= 1024 && sizeof(sm.lens) == 328,
+                  "builder scratch + lens (and the long-code lists in front of them) double as the 16-byte "
+                  "aligned block buffer of copy_match");
     const Grp<G> g;
     if (FORMAT == BDF_GZIP) {
         for (unsigned i = threadIdx.x; i < 1024; i += blockDim.x) s_crc[i >> 8][i & 255] = g_crc_tables.slice[i >> 8][i & 255];
@@ -1176,6 +1192,7 @@ inflate_kernel(InflateArgs a)
         o.pos = 0;
         o.cap = cap64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)cap64;
         o.npend = 0; o.mylit = 0; o.sumA = 0; o.sumB = 0; o.next_fold = ADLER_FOLD_INTERVAL;
+        o.blkcap = BLOCK_BUF_SCRATCH<G>;
         {
             // whole sectors owned by this stream: [first 32-byte boundary at or after out, last one at or before out + cap)
             const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(o.out) & 31u);
