@@ -28,7 +28,7 @@ namespace bdf {
 
 constexpr int HC_THREADS = 128;
 constexpr int HC_WARPS = HC_THREADS / 32;
-constexpr uint32_t HC_WINDOW = 256;           // positions searched per round (max)
+constexpr uint32_t HC_WINDOW = 1024;          // positions searched per round (max): fewer CTA barriers, better balance
 
 // Symbol records written by the parse and consumed by the emitter, in stream order:
 // a literal is its byte value; a match is a length record followed by an offset record.
