@@ -6,10 +6,12 @@
 //   BatchDecompressor::new() / decompress_batch(&[&[u8]], &[usize]) -> Vec<Option<Vec<u8>>> (:70,:74-101)
 //       a stream that fails yields std::nullopt                                     (:95-96)
 //       result length = min(inputs, max_out_sizes)  (zip, :79-81)
-// plus the `format` selector of the C ABI.  Header-only; link with libbdeflate.so.
+// plus the `format` selector of the C ABI, the safe API of src/api.rs (Compressor / Decompressor)
+// and the stream encoder of src/stream.rs (DeflateEncoder).  Header-only; link with libbdeflate.so.
 // A call-level failure (no GPU, CUDA error, unsupported request) throws — there
 // is no CPU fallback behind this API.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -125,6 +127,131 @@ public:
 
 private:
     int format_;
+    std::shared_ptr<Context> ctx_;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Safe API of the reference (src/api.rs): same names, argument meaning and error behaviour.
+//   Compressor::new(level): level outside 0..=12 -> InvalidInput                      (:10-16)
+//   Decompressor: expected_size > len * limit_ratio + 4096 -> InvalidInput "safety limit",
+//                 expected_size > max_memory_limit -> InvalidInput "maximum memory limit" (:213-239)
+//   failures of the codec itself -> InvalidData / "Compression failed"
+// InvalidInput maps to std::invalid_argument, the others to std::runtime_error.
+class Compressor {
+public:
+    explicit Compressor(int level, std::shared_ptr<Context> ctx = nullptr) : level_(level), ctx_(std::move(ctx))
+    {
+        if (level < 0 || level > 12) throw std::invalid_argument("Compression level must be between 0 and 12");
+    }
+    Bytes compress_deflate(ByteView data) { return one(BDF_RAW, data); }
+    Bytes compress_zlib(ByteView data) { return one(BDF_ZLIB, data); }
+    Bytes compress_gzip(ByteView data) { return one(BDF_GZIP, data); }
+    size_t deflate_compress_bound(size_t n) const { return bdf_compress_bound(BDF_RAW, n); }
+    size_t zlib_compress_bound(size_t n) const { return bdf_compress_bound(BDF_ZLIB, n); }
+    size_t gzip_compress_bound(size_t n) const { return bdf_compress_bound(BDF_GZIP, n); }
+
+private:
+    Bytes one(int format, ByteView data)
+    {
+        if (!ctx_) ctx_ = std::make_shared<Context>();
+        auto out = BatchCompressor((size_t)level_, format, ctx_).compress_batch({data});
+        if (out[0].empty() && !(level_ == 0 && data.second == 0 && format == BDF_RAW))
+            throw std::runtime_error("Compression failed");
+        return std::move(out[0]);
+    }
+    int level_;
+    std::shared_ptr<Context> ctx_;
+};
+
+class Decompressor {
+public:
+    explicit Decompressor(std::shared_ptr<Context> ctx = nullptr) : ctx_(std::move(ctx)) {}
+    void set_max_memory_limit(size_t limit) { max_memory_limit_ = limit; }
+    void set_limit_ratio(size_t ratio) { limit_ratio_ = ratio; }
+    Bytes decompress_deflate(ByteView data, size_t expected_size) { return one(BDF_RAW, data, expected_size); }
+    Bytes decompress_zlib(ByteView data, size_t expected_size) { return one(BDF_ZLIB, data, expected_size); }
+    Bytes decompress_gzip(ByteView data, size_t expected_size) { return one(BDF_GZIP, data, expected_size); }
+
+private:
+    static size_t sat_mul(size_t a, size_t b) { return b && a > SIZE_MAX / b ? SIZE_MAX : a * b; }
+    static size_t sat_add(size_t a, size_t b) { return a > SIZE_MAX - b ? SIZE_MAX : a + b; }
+    Bytes one(int format, ByteView data, size_t expected_size)
+    {
+        const size_t limit = sat_add(sat_mul(data.second, limit_ratio_), 4096);
+        if (expected_size > limit)
+            throw std::invalid_argument("Expected size " + std::to_string(expected_size) +
+                                        " exceeds safety limit for input size " + std::to_string(data.second));
+        if (expected_size > max_memory_limit_)
+            throw std::invalid_argument("Expected size " + std::to_string(expected_size) +
+                                        " exceeds maximum memory limit " + std::to_string(max_memory_limit_));
+        if (!ctx_) ctx_ = std::make_shared<Context>();
+        auto out = BatchDecompressor(format, ctx_).decompress_batch({data}, {expected_size});
+        if (!out[0]) throw std::runtime_error("Decompression failed");
+        return std::move(*out[0]);
+    }
+    size_t max_memory_limit_ = SIZE_MAX, limit_ratio_ = 2000;
+    std::shared_ptr<Context> ctx_;
+};
+
+// ---------------------------------------------------------------------------------------------
+// DeflateEncoder of the reference (src/stream.rs:15-240): bytes are buffered (1 MiB by default), a
+// full buffer is cut into 256 KiB chunks, every chunk goes through a fresh compressor and ends in
+// a sync flush, the last chunk of finish() ends the stream.  All chunks of a buffer are ONE
+// bdf_compress_units_host call.  `Sink` needs write(const uint8_t*, size_t) and flush().
+template <class Sink>
+class DeflateEncoder {
+public:
+    DeflateEncoder(Sink &sink, size_t level, std::shared_ptr<Context> ctx = nullptr)
+        : sink_(&sink), level_((int)(level > 12 ? 12 : level)), ctx_(ctx ? ctx : std::make_shared<Context>())
+    {
+        buffer_.reserve(buffer_size_);
+    }
+    ~DeflateEncoder()
+    {
+        if (sink_) try { flush_buffer(true); } catch (...) {}        // Drop, :234-240: errors are ignored
+    }
+    DeflateEncoder &with_buffer_size(size_t n) { buffer_size_ = n; return *this; }
+    size_t write(const uint8_t *p, size_t n)
+    {
+        buffer_.insert(buffer_.end(), p, p + n);
+        if (buffer_.size() >= buffer_size_) flush_buffer(false);
+        return n;
+    }
+    void flush() { flush_buffer(false); sink_->flush(); }
+    void finish() { flush_buffer(true); sink_ = nullptr; }
+
+private:
+    void flush_buffer(bool final_block)
+    {
+        if (buffer_.empty() && !final_block) return;
+        constexpr size_t CHUNK = 256 * 1024;
+        const size_t n = buffer_.empty() ? 1 : (buffer_.size() + CHUNK - 1) / CHUNK;
+        std::vector<uint64_t> off(n + 1), out_off(n), out_size(n);
+        std::vector<uint8_t> mode(n, (uint8_t)BDF_FLUSH_SYNC);
+        std::vector<int32_t> status(n);
+        uint64_t total = 0;
+        for (size_t i = 0; i < n; i++) {
+            off[i] = i * CHUNK;
+            const size_t len = std::min(buffer_.size() - off[i], CHUNK);
+            out_off[i] = total;
+            total += bdf_compress_bound(BDF_RAW, len) + 5;
+        }
+        off[n] = buffer_.size();
+        if (final_block) mode[n - 1] = (uint8_t)BDF_FLUSH_FINISH;
+        Bytes slab(total), dummy(1);
+        ctx_->check(bdf_compress_units_host(ctx_->get(), level_, buffer_.empty() ? dummy.data() : buffer_.data(),
+                                            off.data(), mode.data(), n, slab.data(), out_off.data(),
+                                            out_size.data(), status.data()));
+        for (size_t i = 0; i < n; i++) {
+            if (status[i] != BDF_OK) throw std::runtime_error("Compression failed");
+            sink_->write(slab.data() + out_off[i], out_size[i]);
+        }
+        buffer_.clear();
+    }
+    Sink *sink_;
+    int level_;
+    size_t buffer_size_ = 1024 * 1024;
+    Bytes buffer_;
     std::shared_ptr<Context> ctx_;
 };
 

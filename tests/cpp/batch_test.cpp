@@ -2,6 +2,7 @@
 // (the host mirror of src/batch.rs).  Built and run by tests/test_gpu_cpp_host.py.
 #include <cstdio>
 #include <cstdlib>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -71,6 +72,69 @@ int main()
         bdf::BatchDecompressor d(BDF_RAW, ctx);
         auto out = d.decompress_batch({{bad, 6}}, {100});
         CHECK(out.size() == 1 && !out[0].has_value());
+    }
+    // safe API: tests/security_limit.rs:5-57,60-107 and the level check of api.rs:10-16
+    {
+        bool threw = false;
+        try { bdf::Compressor bad(13); } catch (const std::invalid_argument &) { threw = true; }
+        CHECK(threw);
+        bdf::Decompressor d(ctx);
+        const std::vector<uint8_t> zeros(10, 0);
+        threw = false;
+        try { d.decompress_deflate({zeros.data(), zeros.size()}, 1000000); }
+        catch (const std::invalid_argument &e) { threw = std::string(e.what()).find("safety limit") != std::string::npos; }
+        CHECK(threw);
+        d.set_max_memory_limit(50u << 20);
+        const std::vector<uint8_t> mb(1 << 20, 0);
+        threw = false;
+        try { d.decompress_deflate({mb.data(), mb.size()}, 100u << 20); }
+        catch (const std::invalid_argument &e) { threw = std::string(e.what()).find("maximum memory limit") != std::string::npos; }
+        CHECK(threw);
+        threw = false;                                   // within the limits: garbage is InvalidData, not InvalidInput
+        try { bdf::Decompressor d2(ctx); d2.decompress_deflate({zeros.data(), zeros.size()}, 20000); }
+        catch (const std::invalid_argument &) { CHECK(false); }
+        catch (const std::runtime_error &) { threw = true; }
+        CHECK(threw);
+        std::string original;
+        for (int i = 0; i < 10; i++) original += "Hello world";
+        bdf::Compressor c(1, ctx);
+        auto comp = c.compress_deflate(view(original));
+        bdf::Decompressor d3(ctx);
+        d3.set_max_memory_limit(1 << 20);
+        auto back = d3.decompress_deflate({comp.data(), comp.size()}, original.size());
+        CHECK(std::string(back.begin(), back.end()) == original);
+        auto z = c.compress_zlib(view(original));
+        auto zb = d3.decompress_zlib({z.data(), z.size()}, original.size());
+        CHECK(std::string(zb.begin(), zb.end()) == original);
+    }
+    // stream encoder: tests/stream_test.rs:41-54 (round trip), tests/buffer_size_test.rs:24-58
+    {
+        struct VecSink {
+            std::vector<uint8_t> data;
+            int flushes = 0;
+            void write(const uint8_t *p, size_t n) { data.insert(data.end(), p, p + n); }
+            void flush() { flushes++; }
+        };
+        std::vector<uint8_t> data(700000);
+        for (size_t i = 0; i < data.size(); i++) data[i] = (uint8_t)((i * 7 + i / 1000) % 251);
+        VecSink sink;
+        {
+            bdf::DeflateEncoder<VecSink> enc(sink, 6, ctx);
+            enc.with_buffer_size(300000);
+            enc.write(data.data(), 150000);
+            CHECK(sink.data.empty());
+            enc.write(data.data() + 150000, 250000);          // 400000 >= 300000: two chunks go out, sync-flushed
+            const size_t n1 = sink.data.size();
+            CHECK(n1 > 0);
+            enc.write(data.data() + 400000, 300000);
+            enc.flush();
+            CHECK(sink.flushes == 1);
+            enc.finish();
+            CHECK(sink.data.size() > n1);
+        }
+        bdf::BatchDecompressor d(BDF_RAW, ctx);
+        auto out = d.decompress_batch({{sink.data.data(), sink.data.size()}}, {data.size()});
+        CHECK(out[0].has_value() && *out[0] == data);
     }
     std::puts("batch_test.cpp: all reference batch tests passed");
     return 0;
