@@ -225,17 +225,35 @@ struct BitSink {
     }
 };
 
+// 8 bytes at any alignment from the aligned words that contain them (a word without a requested
+// byte is never touched)
+__device__ __forceinline__ uint64_t ld64_any(const uint8_t *p)
+{
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(p - sh);
+    const uint32_t w0 = w[0], w1 = w[1];
+    if (sh == 0) return (uint64_t)w1 << 32 | w0;
+    const uint32_t w2 = w[2];
+    return (uint64_t)__funnelshift_r(w1, w2, 8 * sh) << 32 | __funnelshift_r(w0, w1, 8 * sh);
+}
+
 // Common-prefix length of a[0..maxlen) and b[0..maxlen), maxlen <= 258, all lanes cooperate
-// (every match_len_* variant of the reference, src/compress/matchfinder.rs:245-694).
+// (every match_len_* variant of the reference, src/compress/matchfinder.rs:245-694).  Each lane
+// compares 8 bytes with one 64-bit XOR (byte-wise only in the last, partial group of eight).
 __device__ __forceinline__ unsigned warp_match_len(const uint8_t *a, const uint8_t *b, unsigned maxlen, unsigned lane)
 {
     for (unsigned base = 0; base < maxlen; base += 256) {
         const unsigned i0 = base + lane * 8;
         unsigned cnt = 0;
+        if (i0 + 8 <= maxlen) {
+            const uint64_t x = ld64_any(a + i0) ^ ld64_any(b + i0);
+            cnt = x ? (unsigned)(__ffsll((long long)x) - 1) >> 3 : 8u;
+        } else {
 #pragma unroll
-        for (unsigned k = 0; k < 8; k++) {
-            unsigned idx = i0 + k;
-            if (cnt == k && idx < maxlen && a[idx] == b[idx]) cnt++;
+            for (unsigned k = 0; k < 7; k++) {
+                unsigned idx = i0 + k;
+                if (cnt == k && idx < maxlen && a[idx] == b[idx]) cnt++;
+            }
         }
         const unsigned stop = __ballot_sync(BDF_FULL_MASK, cnt != 8);
         if (stop) {
