@@ -291,6 +291,23 @@ int bdf_decompress_batch_host(bdf_ctx *ctx, int format, const uint8_t *in, const
 }
 
 // ------------------------------------------------------------------ compress
+static int compress_device_locked(bdf_ctx *ctx, int level, int format, const uint8_t *in, const uint64_t *in_off,
+                                  size_t n, uint8_t *out, const uint64_t *out_off, uint64_t *out_size,
+                                  int32_t *status, cudaStream_t s)
+{
+    bdf::DeflateArgs a;
+    a.in = in; a.in_off = in_off; a.out = out; a.out_off = out_off; a.out_size = out_size; a.status = status;
+    a.n = (uint32_t)n; a.level = level > 12 ? 12 : level; a.format = format; a.unit_flags = nullptr;
+    a.work_counter = next_counter(ctx, s);
+    int nl = 0;
+    const char *why = nullptr;
+    cudaError_t e = bdf::launch_deflate(a, ctx->deflate_scratch, ctx->sm_count, s, &nl, &why);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail(ctx, BDF_E_CUDA, why ? why : "launch_deflate", e);
+    if (why) return fail(ctx, BDF_E_UNSUPPORTED, why);
+    return BDF_E_OK;
+}
+
 int bdf_compress_batch_device(bdf_ctx *ctx, int level, int format, const uint8_t *in, const uint64_t *in_off,
                               size_t n, uint8_t *out, const uint64_t *out_off, uint64_t *out_size,
                               int32_t *status, void *stream)
@@ -304,17 +321,7 @@ int bdf_compress_batch_device(bdf_ctx *ctx, int level, int format, const uint8_t
     if (n > 0xFFFFFFF0ull) return fail(ctx, BDF_E_ARG, "too many streams");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    bdf::DeflateArgs a;
-    a.in = in; a.in_off = in_off; a.out = out; a.out_off = out_off; a.out_size = out_size; a.status = status;
-    a.n = (uint32_t)n; a.level = level > 12 ? 12 : level; a.format = format; a.unit_flags = nullptr;
-    a.work_counter = next_counter(ctx, s);
-    int nl = 0;
-    const char *why = nullptr;
-    cudaError_t e = bdf::launch_deflate(a, ctx->deflate_scratch, ctx->sm_count, s, &nl, &why);
-    ctx->launches += nl;
-    if (e != cudaSuccess) return fail(ctx, BDF_E_CUDA, why ? why : "launch_deflate", e);
-    if (why) return fail(ctx, BDF_E_UNSUPPORTED, why);
-    return BDF_E_OK;
+    return compress_device_locked(ctx, level, format, in, in_off, n, out, out_off, out_size, status, s);
 }
 
 // Streams above 64 KiB: units of at most 256 KiB (Compressor::compress, src/compress/mod.rs:699-772)
@@ -402,8 +409,10 @@ int bdf_compress_batch_host(bdf_ctx *ctx, int level, int format, const uint8_t *
         if (in_off[i + 1] - in_off[i] > max_len) max_len = in_off[i + 1] - in_off[i];
     // level 0 needs the unit path only above one chunk (the stored kernel handles any length)
     const bool chunked = max_len > (level == 0 ? 256u * 1024u : 65536u);
+    // one lock for the whole call: the staging buffers of the ctx are shared by all callers
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaStream_t s = ctx->stream;
     {
-        std::lock_guard<std::mutex> g(ctx->mu);
         CK(cudaSetDevice(ctx->device));
         in_bytes = (size_t)in_off[n];
         for (size_t i = 0; i < n; i++) {
@@ -416,7 +425,6 @@ int bdf_compress_batch_host(bdf_ctx *ctx, int level, int format, const uint8_t *
             (rc = ensure(ctx, ctx->in_off, (n + 1) * 8)) || (rc = ensure(ctx, ctx->out_off, n * 8)) ||
             (rc = ensure(ctx, ctx->out_size, n * 8)) || (rc = ensure(ctx, ctx->status, n * 4)))
             return rc;
-        cudaStream_t s = ctx->stream;
         CK(cudaMemcpyAsync(ctx->in.p, in, in_bytes, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ctx->in_off.p, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ctx->out_off.p, out_off, n * 8, cudaMemcpyHostToDevice, s));
@@ -429,13 +437,11 @@ int bdf_compress_batch_host(bdf_ctx *ctx, int level, int format, const uint8_t *
     }
     int rc = BDF_E_OK;
     if (!chunked)
-        rc = bdf_compress_batch_device(ctx, level, format, (const uint8_t *)ctx->in.p,
-                                       (const uint64_t *)ctx->in_off.p, n, (uint8_t *)ctx->out.p,
-                                       (const uint64_t *)ctx->out_off.p, (uint64_t *)ctx->out_size.p,
-                                       (int32_t *)ctx->status.p, nullptr);
+        rc = compress_device_locked(ctx, level, format, (const uint8_t *)ctx->in.p,
+                                    (const uint64_t *)ctx->in_off.p, n, (uint8_t *)ctx->out.p,
+                                    (const uint64_t *)ctx->out_off.p, (uint64_t *)ctx->out_size.p,
+                                    (int32_t *)ctx->status.p, s);
     if (rc) return rc;
-    std::lock_guard<std::mutex> g(ctx->mu);
-    cudaStream_t s = ctx->stream;
     CK(cudaEventRecord(ctx->ev1, s));
     CK(cudaMemcpyAsync(out_size, ctx->out_size.p, n * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(status, ctx->status.p, n * 4, cudaMemcpyDeviceToHost, s));
@@ -528,17 +534,9 @@ int bdf_compress_units_host(bdf_ctx *ctx, int level, const uint8_t *in, const ui
 }
 
 // ------------------------------------------------------------------ checksum
-int bdf_checksum_batch_device(bdf_ctx *ctx, int kind, const uint8_t *in, const uint64_t *in_off, size_t n,
-                              uint32_t *out, void *stream)
+static int checksum_device_locked(bdf_ctx *ctx, int kind, const uint8_t *in, const uint64_t *in_off, size_t n,
+                                  uint32_t *out, cudaStream_t s)
 {
-    if (!ctx) return BDF_E_ARG;
-    std::lock_guard<std::mutex> g(ctx->mu);
-    if (kind != BDF_ADLER32 && kind != BDF_CRC32) return fail(ctx, BDF_E_ARG, "unknown checksum kind");
-    if (n == 0) return BDF_E_OK;
-    if (!in || !in_off || !out) return fail(ctx, BDF_E_ARG, "null pointer");
-    if (n > 0xFFFFFFF0ull) return fail(ctx, BDF_E_ARG, "too many streams");
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     bdf::ChecksumArgs a{in, in_off, out, (uint32_t)n};
     unsigned long long want = (n + bdf::CK_WARPS_PER_BLOCK - 1) / bdf::CK_WARPS_PER_BLOCK;
     unsigned long long full = (unsigned long long)ctx->sm_count * 8;
@@ -552,30 +550,43 @@ int bdf_checksum_batch_device(bdf_ctx *ctx, int kind, const uint8_t *in, const u
     return BDF_E_OK;
 }
 
+int bdf_checksum_batch_device(bdf_ctx *ctx, int kind, const uint8_t *in, const uint64_t *in_off, size_t n,
+                              uint32_t *out, void *stream)
+{
+    if (!ctx) return BDF_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (kind != BDF_ADLER32 && kind != BDF_CRC32) return fail(ctx, BDF_E_ARG, "unknown checksum kind");
+    if (n == 0) return BDF_E_OK;
+    if (!in || !in_off || !out) return fail(ctx, BDF_E_ARG, "null pointer");
+    if (n > 0xFFFFFFF0ull) return fail(ctx, BDF_E_ARG, "too many streams");
+    CK(cudaSetDevice(ctx->device));
+    return checksum_device_locked(ctx, kind, in, in_off, n, out, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
 int bdf_checksum_batch_host(bdf_ctx *ctx, int kind, const uint8_t *in, const uint64_t *in_off, size_t n,
                             uint32_t *out)
 {
     if (!ctx) return BDF_E_ARG;
+    if (kind != BDF_ADLER32 && kind != BDF_CRC32) return fail(ctx, BDF_E_ARG, "unknown checksum kind");
     if (n == 0) return BDF_E_OK;
     if (!in || !in_off || !out) return fail(ctx, BDF_E_ARG, "null pointer");
-    {
-        std::lock_guard<std::mutex> g(ctx->mu);
-        CK(cudaSetDevice(ctx->device));
-        int rc;
-        if ((rc = ensure(ctx, ctx->in, (size_t)in_off[n] + 8)) || (rc = ensure(ctx, ctx->in_off, (n + 1) * 8)) ||
-            (rc = ensure(ctx, ctx->checksum, n * 4)))
-            return rc;
-        CK(cudaMemcpyAsync(ctx->in.p, in, (size_t)in_off[n], cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->in_off.p, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    }
-    int rc = bdf_checksum_batch_device(ctx, kind, (const uint8_t *)ctx->in.p, (const uint64_t *)ctx->in_off.p, n,
-                                       (uint32_t *)ctx->checksum.p, nullptr);
+    if (n > 0xFFFFFFF0ull) return fail(ctx, BDF_E_ARG, "too many streams");
+    std::lock_guard<std::mutex> g(ctx->mu);      // whole call: the staging buffers are shared
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, ctx->in, (size_t)in_off[n] + 8)) || (rc = ensure(ctx, ctx->in_off, (n + 1) * 8)) ||
+        (rc = ensure(ctx, ctx->checksum, n * 4)))
+        return rc;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->in.p, in, (size_t)in_off[n], cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->in_off.p, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(ctx->ev0, s));
+    rc = checksum_device_locked(ctx, kind, (const uint8_t *)ctx->in.p, (const uint64_t *)ctx->in_off.p, n,
+                                (uint32_t *)ctx->checksum.p, s);
     if (rc) return rc;
-    std::lock_guard<std::mutex> g(ctx->mu);
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    CK(cudaMemcpyAsync(out, ctx->checksum.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventRecord(ctx->ev1, s));
+    CK(cudaMemcpyAsync(out, ctx->checksum.p, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
     return BDF_E_OK;
 }
