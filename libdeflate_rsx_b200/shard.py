@@ -61,3 +61,54 @@ def gather_results(local, n_total, ranges, group=None):
     for r, (lo, hi) in enumerate(ranges):
         full[lo:hi] = outs[r].cpu().numpy().view(local.dtype)[:hi - lo]
     return full
+
+
+class ShardedBatch:
+    """One process, several GPUs: the batch API of src/batch.rs with the streams split over the
+    devices of the box (contiguous ranges balanced by bytes, `partition`), one `bdf_ctx` and one
+    host thread per device, results concatenated in stream order.  No collective: the shards never
+    talk to each other.  This is what a single-process caller (the Rust crate behind the C ABI) does;
+    `bench.py --gpus N` uses one process per GPU instead."""
+
+    def __init__(self, devices=None, context_factory=None):
+        from . import _native as N
+        from .batch import Context
+        if devices is None:
+            devices = list(range(N.lib().bdf_device_count()))
+        if not devices:
+            raise N.BdfError("no CUDA device: the engine has no CPU fallback")
+        make = context_factory or Context
+        self.contexts = [make(d) for d in devices]
+
+    def _run(self, inputs, fn):
+        """fn(ctx, lo, hi) -> list of per-stream results for streams [lo, hi)."""
+        from concurrent.futures import ThreadPoolExecutor
+        n = len(inputs)
+        if n == 0:
+            return []
+        lens = np.array([len(b) for b in inputs], dtype=np.uint64)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(lens)
+        ranges = partition(off, len(self.contexts))
+        with ThreadPoolExecutor(len(self.contexts)) as pool:
+            futs = [pool.submit(fn, ctx, lo, hi) if hi > lo else None
+                    for ctx, (lo, hi) in zip(self.contexts, ranges)]
+            out = []
+            for f in futs:
+                out += f.result() if f is not None else []
+        return out
+
+    def compress_batch(self, inputs, level, format=0):
+        from .batch import BatchCompressor
+        return self._run(inputs, lambda ctx, lo, hi: BatchCompressor(level, format, ctx).compress_batch(inputs[lo:hi]))
+
+    def decompress_batch(self, inputs, max_out_sizes, format=0):
+        from .batch import BatchDecompressor
+        n = min(len(inputs), len(max_out_sizes))
+        inputs, sizes = list(inputs[:n]), list(max_out_sizes[:n])
+        return self._run(inputs, lambda ctx, lo, hi: BatchDecompressor(format, ctx).decompress_batch(
+            inputs[lo:hi], sizes[lo:hi]))
+
+    def checksum_batch(self, inputs, kind):
+        from .batch import checksum_batch
+        return self._run(inputs, lambda ctx, lo, hi: checksum_batch(inputs[lo:hi], kind, ctx))

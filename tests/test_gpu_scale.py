@@ -86,3 +86,18 @@ def test_concurrent_callers_share_one_context(engine):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_sharded_batch_over_all_devices(engine):
+    """Single-process sharding over every GPU of the box (1 on the standard test box, N under
+    `gpurun --gpus N`): one ctx + one host thread per device, results in stream order."""
+    from libdeflate_rsx_b200 import shard
+    sb = shard.ShardedBatch()
+    assert len(sb.contexts) >= 1
+    bufs = [corpus.corpus_b_stream(k, 2000 + 997 * (k % 23)) for k in range(200)] + [b"", b"z"]
+    comp = sb.compress_batch(bufs, 6, 2)
+    exp = {}
+    for i in range(0, len(bufs), 13):
+        assert comp[i] == exp.setdefault(i, o.compress(bufs[i], 6, 2))
+    assert sb.decompress_batch(comp, [len(b) for b in bufs], 2) == bufs
+    assert sb.checksum_batch(bufs, engine.CRC32) == [zlib.crc32(b) for b in bufs]

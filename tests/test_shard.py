@@ -76,3 +76,35 @@ def test_world_size_2_gloo_matches_single_process():
     assert sizes == [len(e) for e in exp]
     assert stats == [0] * len(bufs)
     assert crcs == [zlib.crc32(b) for b in bufs]
+
+
+def test_sharded_batch_orders_results_without_a_gpu():
+    """Host logic of the single-process multi-GPU mirror: partitioning, one worker per device,
+    order-preserving concatenation — with a fake context (no GPU here) and the oracle as the codec."""
+    import libdeflate_rsx_b200.batch as batch
+
+    class FakeCtx:
+        def __init__(self, device):
+            self.device = device
+
+    calls = []
+
+    class FakeCompressor:
+        def __init__(self, level, format, ctx):
+            self.level, self.format, self.ctx = level, format, ctx
+
+        def compress_batch(self, bufs):
+            calls.append((self.ctx.device, len(bufs)))
+            return [o.compress(b, self.level, self.format) or b"" for b in bufs]
+
+    real = batch.BatchCompressor
+    batch.BatchCompressor = FakeCompressor
+    try:
+        sb = shard.ShardedBatch(devices=[0, 1, 2], context_factory=FakeCtx)
+        bufs = [corpus.corpus_b_stream(k, 500 + 300 * k) for k in range(17)] + [b""]
+        got = sb.compress_batch(bufs, 6, 1)
+        assert got == [o.compress(b, 6, 1) for b in bufs]
+        assert sorted(d for d, _ in calls) == [0, 1, 2] and sum(c for _, c in calls) == len(bufs)
+        assert sb.compress_batch([], 6) == []
+    finally:
+        batch.BatchCompressor = real
