@@ -28,6 +28,7 @@ namespace bdf {
 
 constexpr int HC_THREADS = 128;
 constexpr int HC_WARPS = HC_THREADS / 32;
+constexpr uint32_t HC_WINDOW_AFTER_JUMP = 4;   // >= lazy depth + 2
 constexpr uint32_t HC_WINDOW = 1024;          // positions searched per round (max): fewer CTA barriers, better balance
 
 // Symbol records written by the parse and consumed by the emitter, in stream order:
@@ -46,7 +47,9 @@ struct __align__(16) HcSmem {
     uint32_t new_obs[14], obs[14];
     uint32_t num_new, num_obs;
     // control words written by thread 0, read by everyone after a barrier
-    uint32_t c_search_from, c_search_to, c_done, c_pos;
+    uint32_t c_search_from, c_search_to, c_done, c_pos, c_ins_from, c_ins_to;
+    uint32_t ins_pos[HC_WARPS][128];   // hc_insert_par: this warp's positions of the next 128, in order
+    uint16_t ins_hash[HC_WARPS][128];
     uint8_t hdr_lens[320];
     uint16_t hdr_items[320];
     uint32_t pre_freq[19], pre_code[19];
@@ -114,6 +117,55 @@ __device__ __forceinline__ void hc_insert_range(const CH &ch, const uint8_t *in,
     }
 }
 
+// The same insertion by all warps of the CTA at once.  Chains of different hash values never
+// touch each other, so warp w takes the positions whose hash is congruent to w modulo HC_WARPS:
+// it gathers them from the next 128 positions (in order) and links them 32 per step.  Every step
+// is a dependent L2 round trip (bucket head read, then written), and one warp inserting 32
+// positions per step was what bounded highly compressible data (config 4 on corpus A: nine
+// steps per 258-byte match); four warps working on four times as many positions per step cut
+// the number of steps by four.
+template <class CH, class S>
+__device__ __forceinline__ void hc_insert_par(const CH &ch, const uint8_t *in, uint32_t len, uint32_t from,
+                                              uint32_t to, unsigned lane, unsigned warp, S &sm)
+{
+    uint32_t *lpos = sm.ins_pos[warp];
+    uint16_t *lhash = sm.ins_hash[warp];
+    for (uint32_t base = from; base < to; base += 128) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t p = base + 32 * k + lane;
+            const bool ok = p < to && p + 3 <= len;
+            uint32_t h = 0;
+            if (ok) h = hash3(ld24(in + p));
+            const bool own = ok && (h & (HC_WARPS - 1)) == warp;
+            const unsigned b = __ballot_sync(BDF_FULL_MASK, own);
+            if (own) {
+                const unsigned at = m + __popc(b & lanemask_lt());
+                lpos[at] = p;
+                lhash[at] = (uint16_t)h;
+            }
+            m += __popc(b);
+        }
+        __syncwarp();
+        for (uint32_t s0 = 0; s0 < m; s0 += 32) {
+            const bool ok = s0 + lane < m;
+            uint32_t p = 0, h = 0x10000u + lane;           // unique key for idle lanes
+            if (ok) { p = lpos[s0 + lane]; h = lhash[s0 + lane]; }
+            const unsigned peers = __match_any_sync(BDF_FULL_MASK, h);
+            const unsigned lower = peers & lanemask_lt();
+            const uint32_t peer_pos = __shfl_sync(BDF_FULL_MASK, p, lower ? 31 - __clz(lower) : 0);
+            if (ok) {
+                const uint32_t prev = lower ? peer_pos : (uint32_t)ch.head[h];
+                ch.link[p] = (prev == CH::NOPOS || p - prev > 0xFFFFu) ? 0 : (uint16_t)(p - prev);
+            }
+            __syncwarp();
+            if (ok && (peers >> lane) == 1u) ch.head[h] = (typename CH::head_t)p;
+            __syncwarp();
+        }
+    }
+}
+
 // 4 bytes at any alignment from the aligned words that contain them (never touches a word
 // without a requested byte, so it stays inside the stream)
 __device__ __forceinline__ uint32_t ld32_any(const uint8_t *p)
@@ -127,7 +179,19 @@ __device__ __forceinline__ uint32_t ld32_any(const uint8_t *p)
 __device__ __forceinline__ unsigned prefix_len_bytes(const uint8_t *a, const uint8_t *b, unsigned maxlen)
 {
     unsigned n = 0;
-    while (n + 4 <= maxlen) {
+    // most candidates differ within the first word: one 4-byte step, then 8 bytes per step (a
+    // 258-byte match of periodic data is 33 steps instead of 65)
+    if (n + 4 <= maxlen) {
+        const uint32_t x = ld32_any(a) ^ ld32_any(b);
+        if (x) return (__ffs(x) - 1) >> 3;
+        n = 4;
+    }
+    while (n + 8 <= maxlen) {
+        const uint64_t x = ld64_any(a + n) ^ ld64_any(b + n);
+        if (x) return n + ((__ffsll((long long)x) - 1) >> 3);
+        n += 8;
+    }
+    if (n + 4 <= maxlen) {
         const uint32_t x = ld32_any(a + n) ^ ld32_any(b + n);
         if (x) return n + ((__ffs(x) - 1) >> 3);
         n += 4;
@@ -329,9 +393,14 @@ __global__ void __launch_bounds__(HC_THREADS) deflate_hc_kernel(DeflateArgs a)
                 // 1. make sure [p, p + window) is inserted, then search it
                 if (warp == 0) {
                     uint32_t to = p + window < len ? p + window : len;
-                    if (to > ins_end) { hc_insert_range(ch, in, len, ins_end, to, lane); ins_end = to; }
-                    if (lane == 0) { sm.c_search_from = p; sm.c_search_to = to; }
+                    if (lane == 0) {
+                        sm.c_ins_from = ins_end; sm.c_ins_to = to > ins_end ? to : ins_end;
+                        sm.c_search_from = p; sm.c_search_to = to;
+                    }
+                    if (to > ins_end) ins_end = to;
                 }
+                __syncthreads();
+                if (sm.c_ins_to > sm.c_ins_from) hc_insert_par(ch, in, len, sm.c_ins_from, sm.c_ins_to, lane, warp, sm);
                 __syncthreads();
                 const uint32_t sfrom = sm.c_search_from, sto = sm.c_search_to;
                 for (uint32_t q = sfrom + tid; q < sto; q += HC_THREADS) {
@@ -419,7 +488,10 @@ __global__ void __launch_bounds__(HC_THREADS) deflate_hc_kernel(DeflateArgs a)
                         if (p >= sto) jumped = l >= 32;
                     }
                     if (p >= len) block_done = true;
-                    window = jumped ? 32 : HC_WINDOW;
+                    // after a long match only a few positions are worth searching (the next one
+                    // is likely another long match, and each of its neighbours costs a 258-byte
+                    // compare that the jump throws away); the window grows back geometrically
+                    window = jumped ? HC_WINDOW_AFTER_JUMP : (window * 4 < HC_WINDOW ? window * 4 : HC_WINDOW);
                     if (lane == 0) { sm.c_done = block_done ? 1u : 0u; sm.c_pos = p; }
                 }
                 __syncthreads();
