@@ -438,7 +438,7 @@ def main():
                     "steps": e2e_steps, "api": "bdf_decompress_batch_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
+                         "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
                          "traffic": (traffic["dram_bytes_per_stream"] * n if traffic else None),
                          "kernel": "bdf::inflate_kernel<BDF_ZLIB>", "peak_source": peak_src,
                          "traffic_source": (f"ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch over "
