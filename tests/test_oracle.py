@@ -189,3 +189,33 @@ def test_golden_digests():
                 assert rec is None
             else:
                 assert rec == [len(c), hashlib.sha256(c).hexdigest()], (name, level)
+
+
+def test_golden_digests_large_inputs_and_units():
+    """Digests of the oracle on inputs above 64 KiB / 256 KiB and of per-chunk flush-mode
+    compression (tests/golden/oracle_digests_large.json)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import gen_oracle_digests_large as gen
+    with open(os.path.join(os.path.dirname(__file__), "golden", "oracle_digests_large.json")) as f:
+        assert gen.generate() == json.load(f)
+
+
+def test_chunked_and_unit_streams_are_valid_deflate():
+    """System zlib inflates what the oracle makes on the large-input paths: the level-1 split path,
+    256 KiB chunks joined by sync flushes, and a sequence of sync-flushed units ended by a finish."""
+    import zlib
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import gen_oracle_digests_large as gen
+    wb = {0: -15, 1: 15, 2: 31}
+    for name, data in gen.inputs():
+        for level in gen.LEVELS:
+            c = o.compress(data, level, level % 3)
+            if c is not None:           # level 0 above 256 KiB overflows its bound: in-band failure
+                assert zlib.decompress(c, wb[level % 3]) == data, (name, level)
+    parts = [corpus.text_stream(1, 90000), corpus.binary_stream(2, 262144), b"tail"]
+    for level in (0, 1, 6):
+        stream = b"".join(o.compress_unit(p, level, i == len(parts) - 1, i != len(parts) - 1)
+                          for i, p in enumerate(parts))
+        assert zlib.decompress(stream, -15) == b"".join(parts)
