@@ -234,3 +234,54 @@ def test_empty_stream_and_context_manager(engine):
     assert zlib.decompress(sink.getvalue(), -15) == b"dropped without finish"
     with pytest.raises(OSError):
         engine.DeflateDecoder(io.BytesIO(b"\x07not deflate")).read()
+
+
+# ------------------------------------------ reference round-trip inputs through the safe API
+def test_reference_offset_patterns_roundtrip(engine):
+    """The 50 periodic-pattern round trips of the reference's tests/offset_tests.rs (inputs from
+    tests/golden/reference_offset_cases.json), through the safe-API mirror; also byte-identity
+    against the oracle, which the reference tests cannot check."""
+    import json
+    import os
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_offset_cases.json")))
+    assert len(cases) == 50 and not any(c.get("unparsed") for c in cases)
+    d = engine.Decompressor()
+    by_level = {}
+    for c in cases:
+        pat = bytes.fromhex(c["pattern_hex"])
+        data = (pat * (c["take"] // len(pat) + 1))[:c["take"]]
+        by_level.setdefault(c["level"], []).append((c, data))
+    for level, items in by_level.items():
+        comp = engine.Compressor(level).compress_deflate_batch([x for _, x in items])
+        back = d.decompress_deflate_batch(comp, [len(x) for _, x in items])
+        for (c, data), z, b in zip(items, comp, back):
+            assert b == data, c["cite"]
+            assert z == o.compress(data, level), c["cite"]
+
+
+def test_reference_parallel_and_unit_roundtrips(engine):
+    """tests/parallel_test.rs (1 MiB, 256 KiB + 1, 10 MiB and 5 MiB ramps: the chunked path) and the
+    round trips / level ordering of tests/unit_tests.rs:70-149."""
+    c6, d = engine.Compressor(6), engine.Decompressor()
+    ramp = bytes(range(256))
+    for n in (1024 * 1024, 256 * 1024 + 1, 10 * 1024 * 1024):          # parallel_test.rs:4-58
+        data = (ramp * (n // 256 + 1))[:n]
+        comp = c6.compress_deflate(data)
+        assert len(comp) > 0 and d.decompress_deflate(comp, n) == data
+    n = 5 * 1024 * 1024
+    z = bytes((np.arange(n, dtype=np.uint64) * 3 % 251).astype(np.uint8))   # :61-76
+    assert d.decompress_zlib(c6.compress_zlib(z), n) == z
+    g = bytes((np.arange(n, dtype=np.uint64) * 7 % 251).astype(np.uint8))   # :79-94
+    assert d.decompress_gzip(c6.compress_gzip(g), n) == g
+    # unit_tests.rs:112-125: level ordering on 10000 x 'a'
+    data = b"a" * 10000
+    c0 = engine.Compressor(0).compress_deflate(data)
+    c1 = engine.Compressor(1).compress_deflate(data)
+    c12 = engine.Compressor(12).compress_deflate(data)
+    assert len(c0) > 10000 and len(c1) < len(c0) and len(c12) <= len(c1)
+    # unit_tests.rs:128-134 and :137-149
+    for f in (d.decompress_deflate, d.decompress_zlib, d.decompress_gzip):
+        with pytest.raises(engine.BdfDataError):
+            f(bytes([0, 1, 2, 3]), 100)
+    for data in (b"Data set 1", b"Data set 2 - different content"):
+        assert d.decompress_deflate(c6.compress_deflate(data), len(data)) == data
