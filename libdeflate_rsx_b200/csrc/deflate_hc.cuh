@@ -29,6 +29,7 @@ namespace bdf {
 constexpr int HC_THREADS = 128;
 constexpr int HC_WARPS = HC_THREADS / 32;
 constexpr uint32_t HC_WINDOW_AFTER_JUMP = 4;   // >= lazy depth + 2
+constexpr uint32_t HC_NSPEC = 4;               // small windows searched per round after a long match (see the kernel)
 constexpr uint32_t HC_WINDOW = 1024;          // positions searched per round (max): fewer CTA barriers, better balance
 
 // Symbol records written by the parse and consumed by the emitter, in stream order:
@@ -47,7 +48,7 @@ struct __align__(16) HcSmem {
     uint32_t new_obs[14], obs[14];
     uint32_t num_new, num_obs;
     // control words written by thread 0, read by everyone after a barrier
-    uint32_t c_search_from, c_search_to, c_done, c_pos, c_ins_from, c_ins_to;
+    uint32_t c_search_from, c_search_to, c_done, c_pos, c_ins_from, c_ins_to, c_nspec;
     uint32_t ins_pos[HC_WARPS][128];   // hc_insert_par: this warp's positions of the next 128, in order
     uint16_t ins_hash[HC_WARPS][128];
     uint8_t hdr_lens[320];
@@ -391,23 +392,45 @@ __global__ void __launch_bounds__(HC_THREADS) deflate_hc_kernel(DeflateArgs a)
             bool block_done = len == 0;
             while (!block_done) {
                 // 1. make sure [p, p + window) is inserted, then search it
+                // After a long match the next round searches HC_NSPEC small windows instead of one: at p
+                // and at p + 258, p + 516, ... — in run-length / periodic data every match has the
+                // maximum length, so the parse lands exactly on the next window and one
+                // insert / search / parse round (three CTA barriers, ~20 k cycles) yields up to
+                // HC_NSPEC matches instead of one.  A window the parse does not land on is ignored;
+                // find_match(q) does not depend on what was inserted behind q, so inserting further
+                // ahead changes nothing.
                 if (warp == 0) {
+                    const uint32_t nspec = window == HC_WINDOW_AFTER_JUMP ? HC_NSPEC : 1u;
                     uint32_t to = p + window < len ? p + window : len;
-                    if (lane == 0) {
-                        sm.c_ins_from = ins_end; sm.c_ins_to = to > ins_end ? to : ins_end;
-                        sm.c_search_from = p; sm.c_search_to = to;
+                    uint32_t ito = to;
+                    if (nspec > 1) {
+                        const uint32_t far = p + 258u * (nspec - 1) + HC_WINDOW_AFTER_JUMP;
+                        ito = far < len ? far : len;
                     }
-                    if (to > ins_end) ins_end = to;
+                    if (lane == 0) {
+                        sm.c_ins_from = ins_end; sm.c_ins_to = ito > ins_end ? ito : ins_end;
+                        sm.c_search_from = p; sm.c_search_to = to; sm.c_nspec = nspec;
+                    }
+                    if (ito > ins_end) ins_end = ito;
                 }
                 __syncthreads();
                 if (sm.c_ins_to > sm.c_ins_from) hc_insert_par(ch, in, len, sm.c_ins_from, sm.c_ins_to, lane, warp, sm);
                 __syncthreads();
-                const uint32_t sfrom = sm.c_search_from, sto = sm.c_search_to;
-                for (uint32_t q = sfrom + tid; q < sto; q += HC_THREADS) {
-                    unsigned l, o;
-                    hc_search(ch, in, len, q, prm, l, o);
-                    sm.mlen[q - sfrom] = (uint16_t)l;
-                    sm.moff[q - sfrom] = (uint16_t)o;
+                const uint32_t sfrom = sm.c_search_from, sto = sm.c_search_to, nspec = sm.c_nspec;
+                if (nspec == 1) {
+                    for (uint32_t q = sfrom + tid; q < sto; q += HC_THREADS) {
+                        unsigned l, o;
+                        hc_search(ch, in, len, q, prm, l, o);
+                        sm.mlen[q - sfrom] = (uint16_t)l;
+                        sm.moff[q - sfrom] = (uint16_t)o;
+                    }
+                } else if (tid < nspec * HC_WINDOW_AFTER_JUMP) {
+                    // results of window w at indices [4w, 4w + 4)
+                    const uint32_t q = sfrom + 258u * (tid / HC_WINDOW_AFTER_JUMP) + (tid % HC_WINDOW_AFTER_JUMP);
+                    unsigned l = 0, o = 0;
+                    if (q < len) hc_search(ch, in, len, q, prm, l, o);
+                    sm.mlen[tid] = (uint16_t)l;
+                    sm.moff[tid] = (uint16_t)o;
                 }
                 __syncthreads();
                 // 2. parse by warp 0 (decide_greedy_sequences).  Literal runs are handled 32 positions
@@ -415,15 +438,21 @@ __global__ void __launch_bounds__(HC_THREADS) deflate_hc_kernel(DeflateArgs a)
                 //    is evaluated exactly where the serial loop would act on it (see n_safe below).
                 if (warp == 0) {
                     bool jumped = false;
+                    for (uint32_t w = 0; w < nspec && !block_done; w++) {
+                    // window w: positions [wfrom, wto), results at index (position + woff)
+                    const uint32_t wfrom = sfrom + 258u * w;
+                    if (p != wfrom) break;                       // the parse did not land on this window
+                    const uint32_t wto = nspec == 1 ? sto : (wfrom + HC_WINDOW_AFTER_JUMP < len ? wfrom + HC_WINDOW_AFTER_JUMP : len);
+                    const uint32_t woff = HC_WINDOW_AFTER_JUMP * w - wfrom;      // modulo 2^32
                     while (p < len) {
                         // lazy look-ups must stay inside the searched window
-                        if (p + prm.lazy >= sto && sto < len) break;
+                        if (p + prm.lazy >= wto && wto < len) break;
                         bool end_block = false;
                         if (lane == 0) end_block = hc_should_end(sm, p - block_start, len - p);
                         end_block = __shfl_sync(BDF_FULL_MASK, end_block, 0);
                         __syncwarp();
                         if (end_block) { block_done = true; break; }
-                        unsigned l = sm.mlen[p - sfrom], o = sm.moff[p - sfrom];
+                        unsigned l = sm.mlen[p + woff], o = sm.moff[p + woff];
                         if (l < 3) {
                             // literals up to the next match start, the window end, or the next position
                             // at which should_end_block could change state
@@ -432,11 +461,11 @@ __global__ void __launch_bounds__(HC_THREADS) deflate_hc_kernel(DeflateArgs a)
                             if (pending < 2048) n_safe = 2048 - pending;
                             else if (len - p <= 5000) n_safe = 0xFFFFFFFFu;
                             else n_safe = 5000 - (p - block_start);     // block_len < 5000 here
-                            uint32_t limit = sto - p < n_safe ? sto : p + n_safe;
+                            uint32_t limit = wto - p < n_safe ? wto : p + n_safe;
                             uint32_t n = 0;
                             for (;;) {
                                 const uint32_t q = p + n + lane;
-                                const bool lit = q < limit && sm.mlen[q - sfrom] < 3;
+                                const bool lit = q < limit && sm.mlen[q + woff] < 3;
                                 const unsigned stop = __ballot_sync(BDF_FULL_MASK, !lit);
                                 const unsigned take = stop ? __ffs(stop) - 1 : 32;
                                 if (lane < take) {
@@ -457,12 +486,12 @@ __global__ void __launch_bounds__(HC_THREADS) deflate_hc_kernel(DeflateArgs a)
                         }
                         unsigned nlit = 0;      // literals emitted by a lazy decision
                         if (prm.lazy >= 1 && p + 1 < len && l < prm.nice_len) {
-                            const unsigned l1 = sm.mlen[p + 1 - sfrom];
+                            const unsigned l1 = sm.mlen[p + 1 + woff];
                             if (l1 > l) {
-                                nlit = 1; l = l1; o = sm.moff[p + 1 - sfrom];
+                                nlit = 1; l = l1; o = sm.moff[p + 1 + woff];
                                 if (prm.lazy >= 2 && p + 2 < len) {
-                                    const unsigned l2 = sm.mlen[p + 2 - sfrom];
-                                    if (l2 > l1) { nlit = 2; l = l2; o = sm.moff[p + 2 - sfrom]; }
+                                    const unsigned l2 = sm.mlen[p + 2 + woff];
+                                    if (l2 > l1) { nlit = 2; l = l2; o = sm.moff[p + 2 + woff]; }
                                 }
                             }
                         }
@@ -485,7 +514,8 @@ __global__ void __launch_bounds__(HC_THREADS) deflate_hc_kernel(DeflateArgs a)
                         __syncwarp();
                         nsym += nlit + 2;
                         p += nlit + l;
-                        if (p >= sto) jumped = l >= 32;
+                        if (p >= wto) jumped = l >= 32;
+                    }
                     }
                     if (p >= len) block_done = true;
                     // after a long match only a few positions are worth searching (the next one
