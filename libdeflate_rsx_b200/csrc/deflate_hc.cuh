@@ -29,7 +29,7 @@ namespace bdf {
 constexpr int HC_THREADS = 128;
 constexpr int HC_WARPS = HC_THREADS / 32;
 constexpr uint32_t HC_WINDOW_AFTER_JUMP = 4;   // >= lazy depth + 2
-constexpr uint32_t HC_NSPEC = 4;               // small windows searched per round after a long match (see the kernel)
+constexpr uint32_t HC_NSPEC = 32;              // small windows searched per round after a long match (see the kernel)
 constexpr uint32_t HC_WINDOW = 1024;          // positions searched per round (max): fewer CTA barriers, better balance
 
 // Symbol records written by the parse and consumed by the emitter, in stream order:
