@@ -111,7 +111,55 @@ __global__ void __launch_bounds__(L1_WARPS * 32) deflate_l1_kernel(DeflateArgs a
         }
 
         uint32_t pos = 0;
+        bool run_mode = false;          // the last match had the maximum length: try a run of them
         while (pos < len) {
+            if (run_mode) {
+                // Run-length / periodic data is one maximum-length match after the other, and a round
+                // of this (serial) parse is a chain of dependent memory round trips.  After a 258-byte
+                // match the 32 lanes therefore speculate on a RUN of such matches: lane k probes
+                // position pos + 258 k as if every lower lane had been inserted (same rule as the
+                // literal speculation below), measures its own match, and the lanes up to the first
+                // one that is not a full-length match are committed — exactly the serial result,
+                // up to 32 matches per round.
+                run_mode = false;
+                const uint32_t q = pos + 258u * lane;
+                const bool act = q + 3 <= len;
+                uint32_t v = 0, h = 0x10000u + lane;
+                if (act) { v = ld24(in + q); h = hash3(v); }
+                const unsigned peers = __match_any_sync(BDF_FULL_MASK, h);
+                const unsigned lower = peers & lanemask_lt();
+                uint32_t cand = CFG::EMPTY;
+                if (act) cand = lower ? pos + 258u * (31 - __clz(lower)) : (uint32_t)table[h];
+                const bool found = act && cand != CFG::EMPTY && q - cand <= 32768u && ld24(in + cand) == v;
+                unsigned mylen = 0;
+                if (found) mylen = prefix_len_bytes(in + cand, in + q, len - q < 258 ? len - q : 258);
+                const unsigned full = __ballot_sync(BDF_FULL_MASK, mylen == 258);
+                const unsigned j = ~full ? __ffs(~full) - 1 : 32;                 // first lane without a full-length match
+                const unsigned jfound = __shfl_sync(BDF_FULL_MASK, (unsigned)found, j & 31);
+                const unsigned nm = j < 32 ? j + (jfound ? 1u : 0u) : 32u;        // matches taken this round
+                if (nm) {
+                    // bucket writes of the probes that really happen (highest lane of a hash wins)
+                    const unsigned committing = __ballot_sync(BDF_FULL_MASK, act && lane < nm);
+                    const unsigned mine = peers & committing;
+                    if (act && lane < nm && (mine >> lane) == 1u) table[h] = (pos_t)q;
+                    uint32_t bits = 0, nb = 0;
+                    if (lane < nm) {
+                        uint32_t b0, n0, b1, n1;
+                        static_len_code(mylen, b0, n0);
+                        static_off_code(q - cand, b1, n1);
+                        bits = b0 | b1 << n0;                                   // <= 13 + 18 bits
+                        nb = n0 + n1;
+                    }
+                    bs.put(bits, nb, lane);
+                    const unsigned last_len = __shfl_sync(BDF_FULL_MASK, mylen, nm - 1);
+                    pos += 258u * (nm - 1) + last_len;
+                    run_mode = last_len == 258;
+                    __syncwarp();
+                    continue;
+                }
+                __syncwarp();
+                // the position is not a match at all: the literal speculation takes it from here
+            }
             const uint32_t p = pos + lane;
             const bool hashable = p + 3 <= len;          // the last two positions are never hashed (:1140)
             uint32_t v = 0, h = 0x10000u + lane;         // unique key for lanes that do not hash
@@ -198,6 +246,7 @@ __global__ void __launch_bounds__(L1_WARPS * 32) deflate_l1_kernel(DeflateArgs a
             static_off_code(mp - mc, b1, n1);
             bs.put(lane == 0 ? b0 : lane == 1 ? b1 : 0, lane == 0 ? n0 : lane == 1 ? n1 : 0, lane);
             pos = mp + mlen;
+            run_mode = !split && mlen == 258;
             __syncwarp();
         }
         bs.put1(0, 7, lane);                     // end of block (symbol 256 = 0000000)
