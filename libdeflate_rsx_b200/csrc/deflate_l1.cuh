@@ -131,10 +131,36 @@ __global__ void __launch_bounds__(L1_WARPS * 32) deflate_l1_kernel(DeflateArgs a
                 uint32_t cand = CFG::EMPTY;
                 if (act) cand = lower ? pos + 258u * (31 - __clz(lower)) : (uint32_t)table[h];
                 const bool found = act && cand != CFG::EMPTY && q - cand <= 32768u && ld24(in + cand) == v;
-                unsigned mylen = 0;
-                if (found) mylen = prefix_len_bytes(in + cand, in + q, len - q < 258 ? len - q : 258);
-                const unsigned full = __ballot_sync(BDF_FULL_MASK, mylen == 258);
+                // Which matches have the full 258 bytes?  The last two bytes are checked by each lane
+                // for its own match; the first 256 are compared by the WHOLE warp, match after match
+                // (one coalesced 256-byte access per side, four matches in flight) — 32 lanes each
+                // walking their own 258 bytes touched 32 sectors per load and left the kernel waiting
+                // on L2 / DRAM (long-scoreboard stall 51 per issue).
+                bool maybe = found && len - q >= 258;
+                if (maybe) maybe = in[cand + 256] == in[q + 256] && in[cand + 257] == in[q + 257];
+                const unsigned cand_ok = __ballot_sync(BDF_FULL_MASK, maybe);
+                unsigned full = 0;
+                for (unsigned m0 = 0; m0 < 32; m0 += 4) {
+                    uint64_t x[4];
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const unsigned m = m0 + t;
+                        const uint32_t cm = __shfl_sync(BDF_FULL_MASK, cand, m), qm = __shfl_sync(BDF_FULL_MASK, q, m);
+                        x[t] = 1;
+                        if ((cand_ok >> m) & 1u) x[t] = ld64_any(in + cm + 8u * lane) ^ ld64_any(in + qm + 8u * lane);
+                    }
+                    bool all4 = true;
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const bool eq = __ballot_sync(BDF_FULL_MASK, x[t] == 0) == BDF_FULL_MASK;
+                        if (eq) full |= 1u << (m0 + t);
+                        all4 = all4 && eq;
+                    }
+                    if (!all4) break;                                          // the run ends in this group of four
+                }
                 const unsigned j = ~full ? __ffs(~full) - 1 : 32;                 // first lane without a full-length match
+                unsigned mylen = lane < j ? 258u : 0u;
+                if (lane == j && found) mylen = prefix_len_bytes(in + cand, in + q, len - q < 258 ? len - q : 258);
                 const unsigned jfound = __shfl_sync(BDF_FULL_MASK, (unsigned)found, j & 31);
                 const unsigned nm = j < 32 ? j + (jfound ? 1u : 0u) : 32u;        // matches taken this round
                 if (nm) {
