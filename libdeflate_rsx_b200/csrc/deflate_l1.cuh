@@ -20,6 +20,7 @@
 namespace bdf {
 
 constexpr int L1_WARPS = 4;                      // streams per CTA
+constexpr int L1_RUN_BATCH = 8;                  // matches of a speculated run verified per memory round trip
 
 // The hash table of each stream (last position per bucket, all-ones = empty; 16-bit positions
 // for the 64 KiB instance, 32-bit for the 256 KiB one) lives in a per-warp global slab that
@@ -133,17 +134,17 @@ __global__ void __launch_bounds__(L1_WARPS * 32) deflate_l1_kernel(DeflateArgs a
                 const bool found = act && cand != CFG::EMPTY && q - cand <= 32768u && ld24(in + cand) == v;
                 // Which matches have the full 258 bytes?  The last two bytes are checked by each lane
                 // for its own match; the first 256 are compared by the WHOLE warp, match after match
-                // (one coalesced 256-byte access per side, four matches in flight) — 32 lanes each
+                // (one coalesced 256-byte access per side, L1_RUN_BATCH matches in flight) — 32 lanes each
                 // walking their own 258 bytes touched 32 sectors per load and left the kernel waiting
                 // on L2 / DRAM (long-scoreboard stall 51 per issue).
                 bool maybe = found && len - q >= 258;
                 if (maybe) maybe = in[cand + 256] == in[q + 256] && in[cand + 257] == in[q + 257];
                 const unsigned cand_ok = __ballot_sync(BDF_FULL_MASK, maybe);
                 unsigned full = 0;
-                for (unsigned m0 = 0; m0 < 32; m0 += 4) {
-                    uint64_t x[4];
+                for (unsigned m0 = 0; m0 < 32; m0 += L1_RUN_BATCH) {
+                    uint64_t x[L1_RUN_BATCH];
 #pragma unroll
-                    for (int t = 0; t < 4; t++) {
+                    for (int t = 0; t < L1_RUN_BATCH; t++) {
                         const unsigned m = m0 + t;
                         const uint32_t cm = __shfl_sync(BDF_FULL_MASK, cand, m), qm = __shfl_sync(BDF_FULL_MASK, q, m);
                         x[t] = 1;
@@ -151,12 +152,12 @@ __global__ void __launch_bounds__(L1_WARPS * 32) deflate_l1_kernel(DeflateArgs a
                     }
                     bool all4 = true;
 #pragma unroll
-                    for (int t = 0; t < 4; t++) {
+                    for (int t = 0; t < L1_RUN_BATCH; t++) {
                         const bool eq = __ballot_sync(BDF_FULL_MASK, x[t] == 0) == BDF_FULL_MASK;
                         if (eq) full |= 1u << (m0 + t);
                         all4 = all4 && eq;
                     }
-                    if (!all4) break;                                          // the run ends in this group of four
+                    if (!all4) break;                                          // the run ends in this group
                 }
                 const unsigned j = ~full ? __ffs(~full) - 1 : 32;                 // first lane without a full-length match
                 unsigned mylen = lane < j ? 258u : 0u;
