@@ -149,6 +149,25 @@ int bdf_compress_units_host(bdf_ctx *ctx, int level, const uint8_t *in, const ui
                             const uint8_t *flush, size_t n, uint8_t *out, const uint64_t *out_off,
                             uint64_t *out_size, int32_t *status);
 
+/*
+ * Compressor::compress_to_size(input, final_block) for many buffers at once
+ * (src/compress/mod.rs:792-1094): out_size[i] = the reference's estimate, in bytes, of buffer i as
+ * raw DEFLATE at `level` — what a caller sizes an output slab with instead of
+ * bdf_compress_bound.  No output slab is needed: the compression kernels run with their bit
+ * sinks in counting mode.  The estimate equals the compressed size at levels 2..9; at level 0 it
+ * is the closed form of :1073-1082 (final_block adds the empty final block of an empty input);
+ * at level 1 it counts the blocks the split statistics would cut (the compressor itself keeps
+ * one block up to 64 KiB); at levels 10..12 it follows the estimator's own two-parse cost
+ * seeding; an empty input costs 0 bytes at levels 1..12.
+ * Buffer length: at most 262144 bytes through the *_host call; the *_device call runs the 64 KiB
+ * instances (262144 at levels 0 and 1) and sets BDF_STREAM_UNSUPPORTED beyond.
+ */
+int bdf_compress_size_batch_device(bdf_ctx *ctx, int level, const uint8_t *in, const uint64_t *in_off,
+                                   size_t n, int final_block, uint64_t *out_size, int32_t *status,
+                                   void *stream);
+int bdf_compress_size_batch_host(bdf_ctx *ctx, int level, const uint8_t *in, const uint64_t *in_off,
+                                 size_t n, int final_block, uint64_t *out_size, int32_t *status);
+
 /* adler32(1, data) / crc32(0, data) per stream (src/adler32/mod.rs:114-152,
  * src/crc32/mod.rs:331-365). */
 int bdf_checksum_batch_device(bdf_ctx *ctx, int kind, const uint8_t *in,

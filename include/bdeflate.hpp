@@ -87,6 +87,25 @@ public:
                 res[i].assign(slab.begin() + out_off[i], slab.begin() + out_off[i] + out_size[i]);
         return res;
     }
+    // Compressor::compress_to_size(input, final_block) per buffer (src/compress/mod.rs:1073-1094):
+    // estimated raw-DEFLATE bytes, no output slab; buffers of at most 256 KiB
+    std::vector<size_t> compress_to_size_batch(const std::vector<ByteView> &inputs, bool final_block = true) const
+    {
+        const size_t n = inputs.size();
+        std::vector<size_t> res(n);
+        if (n == 0) return res;
+        Bytes flat;
+        std::vector<uint64_t> in_off, out_size(n);
+        std::vector<int32_t> status(n);
+        detail::flatten(inputs, n, flat, in_off);
+        ctx_->check(bdf_compress_size_batch_host(ctx_->get(), level_, flat.data(), in_off.data(), n,
+                                                 final_block ? 1 : 0, out_size.data(), status.data()));
+        for (size_t i = 0; i < n; i++) {
+            if (status[i] != BDF_OK) throw std::runtime_error("compress_to_size: buffer not supported");
+            res[i] = (size_t)out_size[i];
+        }
+        return res;
+    }
 
 private:
     int level_, format_;

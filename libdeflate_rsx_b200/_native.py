@@ -21,6 +21,7 @@ EXPORTS = [
     "bdf_compress_bound", "bdf_decompress_batch_device", "bdf_decompress_batch_host",
     "bdf_compress_batch_device", "bdf_compress_batch_host", "bdf_checksum_batch_device",
     "bdf_checksum_batch_host", "bdf_gather_streams_device", "bdf_compress_units_host",
+    "bdf_compress_size_batch_device", "bdf_compress_size_batch_host",
 ]
 
 
@@ -67,6 +68,10 @@ def load():
     L.bdf_checksum_batch_host.argtypes = [vp, C.c_int, vp, vp, sz, vp]
     L.bdf_compress_units_host.restype = C.c_int
     L.bdf_compress_units_host.argtypes = [vp, C.c_int, vp, vp, vp, sz, vp, vp, vp, vp]
+    L.bdf_compress_size_batch_device.restype = C.c_int
+    L.bdf_compress_size_batch_device.argtypes = [vp, C.c_int, vp, vp, sz, C.c_int, vp, vp, vp]
+    L.bdf_compress_size_batch_host.restype = C.c_int
+    L.bdf_compress_size_batch_host.argtypes = [vp, C.c_int, vp, vp, sz, C.c_int, vp, vp]
     L.bdf_gather_streams_device.restype = C.c_int
     L.bdf_gather_streams_device.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
     return L

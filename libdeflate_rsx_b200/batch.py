@@ -132,6 +132,23 @@ class BatchCompressor:
         return res
 
 
+    def compress_to_size_batch(self, inputs, final_block=True):
+        """Compressor::compress_to_size (src/compress/mod.rs:1073-1094) per buffer: the estimated
+        raw-DEFLATE size in bytes, no output slab needed.  Buffers of at most 256 KiB."""
+        if len(inputs) == 0:
+            return []
+        flat, in_off = flatten(inputs)
+        n = len(inputs)
+        out_size = np.zeros(n, dtype=np.uint64)
+        status = np.zeros(n, dtype=np.int32)
+        self.ctx.check(self.ctx._lib.bdf_compress_size_batch_host(
+            self.ctx.handle, self.level, _ptr(flat), _ptr(in_off), n, int(bool(final_block)),
+            _ptr(out_size), _ptr(status)))
+        if (status != N.OK).any():
+            raise N.BdfError("compress_to_size: stream %d unsupported" % int(np.nonzero(status)[0][0]))
+        return [int(v) for v in out_size]
+
+
 class BatchDecompressor:
     def __init__(self, format=N.RAW, context=None):
         self.format = int(format)

@@ -552,6 +552,76 @@ int bdf_compress_units_host(bdf_ctx *ctx, int level, const uint8_t *in, const ui
     return BDF_E_OK;
 }
 
+// ---------------------------------------------------------- size estimation
+static int compress_size_locked(bdf_ctx *ctx, int level, const uint8_t *in, const uint64_t *in_off, size_t n,
+                                int final_block, uint64_t *out_size, int32_t *status, uint64_t max_len,
+                                cudaStream_t s)
+{
+    bdf::DeflateArgs a;
+    a.in = in; a.in_off = in_off; a.out = nullptr; a.out_off = nullptr; a.out_size = out_size; a.status = status;
+    a.n = (uint32_t)n; a.level = level > 12 ? 12 : level; a.format = BDF_RAW; a.unit_flags = nullptr;
+    a.size_only = 1; a.final_block = final_block ? 1 : 0;
+    a.work_counter = next_counter(ctx, s);
+    int nl = 0;
+    const char *why = nullptr;
+    cudaError_t e = bdf::launch_deflate(a, ctx->deflate_scratch, ctx->sm_count, s, &nl, &why, max_len);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail(ctx, BDF_E_CUDA, why ? why : "launch_deflate", e);
+    if (why) return fail(ctx, BDF_E_UNSUPPORTED, why);
+    return BDF_E_OK;
+}
+
+int bdf_compress_size_batch_device(bdf_ctx *ctx, int level, const uint8_t *in, const uint64_t *in_off,
+                                   size_t n, int final_block, uint64_t *out_size, int32_t *status,
+                                   void *stream)
+{
+    if (!ctx) return BDF_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (level < 0) return fail(ctx, BDF_E_ARG, "negative level");
+    if (n == 0) return BDF_E_OK;
+    if (!in || !in_off || !out_size || !status) return fail(ctx, BDF_E_ARG, "null pointer");
+    if (n > 0xFFFFFFF0ull) return fail(ctx, BDF_E_ARG, "too many streams");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    return compress_size_locked(ctx, level, in, in_off, n, final_block, out_size, status, 0, s);
+}
+
+int bdf_compress_size_batch_host(bdf_ctx *ctx, int level, const uint8_t *in, const uint64_t *in_off,
+                                 size_t n, int final_block, uint64_t *out_size, int32_t *status)
+{
+    if (!ctx) return BDF_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (level < 0) return fail(ctx, BDF_E_ARG, "negative level");
+    if (n == 0) return BDF_E_OK;
+    if (!in || !in_off || !out_size || !status) return fail(ctx, BDF_E_ARG, "null pointer");
+    if (n > 0xFFFFFFF0ull) return fail(ctx, BDF_E_ARG, "too many streams");
+    uint64_t max_len = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t l = in_off[i + 1] - in_off[i];
+        if (l > max_len) max_len = l;
+    }
+    if (level > 0 && max_len > 256u * 1024u) return fail(ctx, BDF_E_ARG, "a buffer is at most 262144 bytes");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t in_bytes = (size_t)in_off[n];
+    int rc;
+    if ((rc = ensure(ctx, ctx->in, in_bytes + 8)) || (rc = ensure(ctx, ctx->in_off, (n + 1) * 8)) ||
+        (rc = ensure(ctx, ctx->out_size, n * 8)) || (rc = ensure(ctx, ctx->status, n * 4)))
+        return rc;
+    CK(cudaMemcpyAsync(ctx->in.p, in, in_bytes, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->in_off.p, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(ctx->ev0, s));
+    rc = compress_size_locked(ctx, level, (const uint8_t *)ctx->in.p, (const uint64_t *)ctx->in_off.p, n,
+                              final_block, (uint64_t *)ctx->out_size.p, (int32_t *)ctx->status.p, max_len, s);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev1, s));
+    CK(cudaMemcpyAsync(out_size, ctx->out_size.p, n * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(status, ctx->status.p, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+    return BDF_E_OK;
+}
+
 // ------------------------------------------------------------------ checksum
 static int checksum_device_locked(bdf_ctx *ctx, int kind, const uint8_t *in, const uint64_t *in_off, size_t n,
                                   uint32_t *out, cudaStream_t s)

@@ -40,6 +40,12 @@ __global__ void __launch_bounds__(L0_WARPS_PER_BLOCK * 32) deflate_stored_kernel
     for (uint32_t idx = blockIdx.x * L0_WARPS_PER_BLOCK + (threadIdx.x >> 5); idx < a.n; idx += warps) {
         const uint8_t *in = a.in + a.in_off[idx];
         const uint64_t len = a.in_off[idx + 1] - a.in_off[idx];
+        if (a.size_only) {
+            // compress_to_size at level 0, src/compress/mod.rs:1073-1082
+            const uint64_t blocks = len / 65535 + ((len % 65535 != 0 || (len == 0 && a.final_block)) ? 1 : 0);
+            if (lane == 0) { a.out_size[idx] = len + blocks * 5; a.status[idx] = BDF_OK; }
+            continue;
+        }
         uint8_t *out = a.out + a.out_off[idx];
         const unsigned uflags = unit_flags_of(a, idx);
         uint64_t op = frame_header(a.format, 0, out, lane);
@@ -123,7 +129,8 @@ __global__ void __launch_bounds__(JOIN_WARPS * 32) deflate_join_kernel(JoinArgs 
 inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm_count, cudaStream_t s,
                                   int *nlaunch, const char **why, uint64_t max_len = 0)
 {
-    const bool big = max_len > 65536;
+    // the level-1 estimator always runs the block-split path, which only the 256 KiB instance holds
+    const bool big = max_len > 65536 || (a.size_only && a.level == 1);
     *nlaunch = 0;
     *why = nullptr;
     cudaError_t e;
@@ -158,7 +165,8 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
         }
         a.scratch = scratch.p;
         a.scratch_stride = per_warp;
-        if (big) deflate_l1_kernel<true><<<grid, L1_WARPS * 32, smem, s>>>(a);
+        if (a.size_only) deflate_l1_kernel<true, true><<<grid, L1_WARPS * 32, smem, s>>>(a);
+        else if (big) deflate_l1_kernel<true><<<grid, L1_WARPS * 32, smem, s>>>(a);
         else deflate_l1_kernel<false><<<grid, L1_WARPS * 32, smem, s>>>(a);
         *nlaunch = 1;
         return cudaGetLastError();
@@ -177,6 +185,10 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
             e = cudaFuncSetAttribute(deflate_hc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess)
                 e = cudaFuncSetAttribute(deflate_hc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(deflate_hc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(deflate_hc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             scratch.hc_ready = true;
             *why = nullptr;
@@ -197,7 +209,9 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
         }
         a.scratch = scratch.p;
         a.scratch_stride = per_cta;
-        if (big) deflate_hc_kernel<true><<<grid, HC_THREADS, smem, s>>>(a);
+        if (a.size_only && big) deflate_hc_kernel<true, true><<<grid, HC_THREADS, smem, s>>>(a);
+        else if (a.size_only) deflate_hc_kernel<false, true><<<grid, HC_THREADS, smem, s>>>(a);
+        else if (big) deflate_hc_kernel<true><<<grid, HC_THREADS, smem, s>>>(a);
         else deflate_hc_kernel<false><<<grid, HC_THREADS, smem, s>>>(a);
         *nlaunch = 1;
         return cudaGetLastError();

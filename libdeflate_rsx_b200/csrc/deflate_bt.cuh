@@ -162,7 +162,8 @@ struct ThreadBits {
         buf |= (uint64_t)bits << cnt;
         cnt += n;
         while (cnt >= 8) {
-            if (pos < cap) out[pos] = (uint8_t)buf;
+            if (!out) {}                                  // size estimation: count only
+            else if (pos < cap) out[pos] = (uint8_t)buf;
             else overflow = true;
             pos++;
             buf >>= 8;
@@ -215,7 +216,7 @@ __device__ void bt_write_block(BtLocal &L, ThreadBits &bs, const uint32_t *syms,
 template <class BT>
 __device__ uint32_t bt_near_optimal_block(BT &bt, BtLocal &L, uint32_t *cost, uint32_t *path, uint32_t *syms,
                                           const uint8_t *in, uint32_t n, uint32_t start, ThreadBits &bs,
-                                          unsigned max_depth, unsigned nice_len, bool finish)
+                                          unsigned max_depth, unsigned nice_len, bool finish, bool size_mode)
 {
     // pass 1: greedy parse with the binary tree -> split point and first costs
     for (int i = 0; i < 288; i++) L.litlen_freq[i] = 0;
@@ -231,7 +232,14 @@ __device__ uint32_t bt_near_optimal_block(BT &bt, BtLocal &L, uint32_t *cost, ui
         if (v.best_len >= 3) {
             const unsigned len = v.best_len, slot = offset_slot_of(v.best_off);
             L.new_obs[8 + (len >= 8)]++;
-            L.new_obs[10 + (slot < 16 ? 0 : slot < 24 ? 1 : slot < 30 ? 2 : 0)]++;
+            if (size_mode) {
+                // the estimator classifies by offset magnitude (observe_match + OFF_IDX_TABLE,
+                // src/compress/mod.rs:107-112,311-330), the compressor by slot
+                const unsigned lg = 31u - (unsigned)__clz(v.best_off);
+                L.new_obs[10 + (lg < 8 ? 0 : lg < 12 ? 1 : lg < 15 ? 2 : 3)]++;
+            } else {
+                L.new_obs[10 + (slot < 16 ? 0 : slot < 24 ? 1 : slot < 30 ? 2 : 0)]++;
+            }
             L.num_new += 2;
             L.litlen_freq[257 + length_slot_of(len)]++;
             L.offset_freq[slot]++;
@@ -249,6 +257,29 @@ __device__ uint32_t bt_near_optimal_block(BT &bt, BtLocal &L, uint32_t *cost, ui
     const uint32_t done = p - start;
     const uint8_t *blk = in + start;
     const bool is_final = start + done >= n && finish;
+    if (size_mode) {
+        // calculate_block_size_near_optimal seeds the costs from a second greedy parse of the
+        // block slice with reset tables (src/compress/mod.rs:902-934)
+        for (int i = 0; i < 288; i++) L.litlen_freq[i] = 0;
+        for (int i = 0; i < 32; i++) L.offset_freq[i] = 0;
+        bt_reset(bt);
+        for (uint32_t q = 0; q < done;) {
+            BtVisitor v;
+            v.mode = 1; v.best_len = 0; v.best_off = 0; v.list = nullptr; v.nlist = 0;
+            bt_advance_one_byte(bt, blk, done, q, max_depth, nice_len, v);
+            if (v.best_len >= 3) {
+                L.litlen_freq[257 + length_slot_of(v.best_len)]++;
+                L.offset_freq[offset_slot_of(v.best_off)]++;
+                BtVisitor nv;
+                nv.mode = 0; nv.best_len = 0; nv.best_off = 0; nv.list = nullptr; nv.nlist = 0;
+                for (unsigned k = 1; k < v.best_len; k++) bt_advance_one_byte(bt, blk, done, q + k, max_depth, nice_len, nv);
+                q += v.best_len;
+            } else {
+                L.litlen_freq[blk[q]]++;
+                q++;
+            }
+        }
+    }
     L.litlen_freq[256]++;
     make_huffman_code_serial(288, 14, L.litlen_freq, L.litlen_len, L.litlen_code, L.scratch);
     make_huffman_code_serial(32, 15, L.offset_freq, L.offset_len, L.offset_code, L.scratch);
@@ -342,13 +373,15 @@ __global__ void __launch_bounds__(BT_THREADS) deflate_bt_kernel(DeflateArgs a)
         if (idx >= a.n) break;
         const uint8_t *in = a.in + a.in_off[idx];
         const uint64_t len64 = a.in_off[idx + 1] - a.in_off[idx];
-        uint8_t *out = a.out + a.out_off[idx];
+        uint8_t *out = a.size_only ? nullptr : a.out + a.out_off[idx];
+        if (a.size_only && len64 == 0) { a.status[idx] = BDF_OK; a.out_size[idx] = 0; continue; }   // :808
         if (len64 > BT::MAX_LEN) { a.status[idx] = BDF_STREAM_UNSUPPORTED; a.out_size[idx] = 0; continue; }
         const unsigned uflags = unit_flags_of(a, idx);
         const uint32_t len = (uint32_t)len64;
         // framing header (compress_zlib / compress_gzip, src/compress/mod.rs:2248-2357)
         unsigned hdr = 0;
-        if (a.format == BDF_ZLIB) {
+        if (!out) {
+        } else if (a.format == BDF_ZLIB) {
             unsigned h = (8u << 8) | (7u << 12) | (3u << 6);
             h |= 31 - (h % 31);
             out[0] = (uint8_t)(h >> 8); out[1] = (uint8_t)h;
@@ -359,12 +392,12 @@ __global__ void __launch_bounds__(BT_THREADS) deflate_bt_kernel(DeflateArgs a)
             hdr = 10;
         }
         ThreadBits bs;
-        bs.out = out + hdr; bs.cap = unit_cap(len, uflags); bs.pos = 0; bs.buf = 0; bs.cnt = 0; bs.overflow = false;
+        bs.out = out ? out + hdr : nullptr; bs.cap = out ? unit_cap(len, uflags) : ~0ull; bs.pos = 0; bs.buf = 0; bs.cnt = 0; bs.overflow = false;
         bt_reset(bt);
         uint32_t p = 0;
         do {
             p += bt_near_optimal_block(bt, L, cost, path, syms, in, len, p, bs, max_depth, nice_len,
-                                       (uflags & UNIT_FINISH) != 0);
+                                       (uflags & UNIT_FINISH) != 0, a.size_only != 0);
         } while (p < len);
         if (uflags & UNIT_SYNC) {
             // FlushMode::Sync, src/compress/mod.rs:662-681
@@ -377,6 +410,7 @@ __global__ void __launch_bounds__(BT_THREADS) deflate_bt_kernel(DeflateArgs a)
         int st = BDF_OK;
         uint64_t sz = bs.pos;
         if (bs.overflow || bs.pos > bs.cap) { st = BDF_INSUFFICIENT_SPACE; sz = 0; }
+        else if (!out) {}
         else if (a.format == BDF_ZLIB) {
             uint32_t s1 = 1, s2 = 0;
             for (uint32_t i = 0; i < len;) {

@@ -26,6 +26,12 @@ struct DeflateArgs {
     // stream (FlushMode::Finish), bit 1 = it is followed by a sync flush (:662-681).  NULL = every
     // entry is a whole stream (finish, no sync).
     const uint8_t *unit_flags;
+    // Size estimation (Compressor::compress_to_size, src/compress/mod.rs:792-1094): the same kernels
+    // run with out == NULL, count bits instead of storing them and follow the estimator's block
+    // rules (level 1 always runs the split statistics, levels 10..12 seed their costs from a second
+    // greedy parse, an empty input costs nothing).  final_block only matters at level 0 (:1073-1082).
+    int size_only = 0;
+    int final_block = 1;
 };
 constexpr unsigned UNIT_FINISH = 1u, UNIT_SYNC = 2u, UNIT_CAP5 = 4u;   // CAP5: 5 more bytes of room (DeflateEncoder, src/stream.rs:66-69)
 __host__ __device__ inline uint64_t unit_cap(uint64_t len, unsigned flags) { return len + (len / 65535 + 1) * 5 + 10 + ((flags & 4u) ? 5 : 0); }
@@ -117,7 +123,9 @@ __device__ __forceinline__ uint32_t hash3(uint32_t v24) { return (v24 * 0x1E35A7
 constexpr uint32_t SINK_WORDS = 512;                 // 2 KiB staging per sink
 constexpr uint32_t SINK_FLUSH_BITS = 8192;           // flush once 1 KiB is pending
 
-struct BitSink {
+// COUNT = true: size estimation, nothing is stored and nothing can overflow.
+template <bool COUNT>
+struct BitSinkT {
     uint32_t *buf;      // shared, SINK_WORDS, zero-filled outside [0, nbits)
     uint8_t *out;       // global destination
     uint64_t cap;       // bytes available at out
@@ -137,7 +145,7 @@ struct BitSink {
         const uint64_t bytes = (uint64_t)nfull * 4;
         __syncwarp();
         if (flushed + bytes > cap) overflow = true;
-        if (!overflow) {
+        if (!COUNT && !overflow) {
             for (uint32_t w = lane; w < nfull; w += 32) {
                 uint32_t v = buf[w];
                 uint8_t *d = out + flushed + 4ull * w;
@@ -193,7 +201,7 @@ struct BitSink {
     __device__ __forceinline__ void set_bit(uint64_t at, unsigned lane)
     {
         __syncwarp();
-        if (lane == 0 && !overflow) {
+        if (lane == 0 && !overflow && (!COUNT || at >= flushed * 8)) {
             if (at >= flushed * 8) {
                 const uint32_t r = (uint32_t)(at - flushed * 8);
                 buf[r >> 5] |= 1u << (r & 31u);
@@ -217,13 +225,15 @@ struct BitSink {
         __syncwarp();
         const uint32_t bytes = (nbits + 7) >> 3;
         if (flushed + bytes > cap) overflow = true;
-        if (!overflow) {
+        if (!COUNT && !overflow) {
             for (uint32_t b = lane; b < bytes; b += 32) out[flushed + b] = (uint8_t)(buf[b >> 2] >> (8 * (b & 3)));
         }
         __syncwarp();
         return overflow ? ~0ull : flushed + bytes;
     }
 };
+
+using BitSink = BitSinkT<false>;
 
 // 8 bytes at any alignment from the aligned words that contain them (a word without a requested
 // byte is never touched)

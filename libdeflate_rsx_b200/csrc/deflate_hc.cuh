@@ -333,7 +333,7 @@ __device__ void hc_prepare_header(S &sm, unsigned &nlit, unsigned &noff, unsigne
     while (npre > 4 && sm.pre_len[perm[npre - 1]] == 0) npre--;
 }
 
-template <bool BIG>
+template <bool BIG, bool SIZE = false>
 __global__ void __launch_bounds__(HC_THREADS) deflate_hc_kernel(DeflateArgs a)
 {
     using CH = HcChains<BIG>;
@@ -357,8 +357,12 @@ __global__ void __launch_bounds__(HC_THREADS) deflate_hc_kernel(DeflateArgs a)
         if (idx >= a.n) break;
         const uint8_t *in = a.in + a.in_off[idx];
         const uint64_t len64 = a.in_off[idx + 1] - a.in_off[idx];
-        uint8_t *out = a.out + a.out_off[idx];
+        uint8_t *out = SIZE ? nullptr : a.out + a.out_off[idx];
         const unsigned uflags = unit_flags_of(a, idx);
+        if (SIZE && len64 == 0) {             // the estimator's block loop never runs (:808)
+            if (tid == 0) { a.status[idx] = BDF_OK; a.out_size[idx] = 0; }
+            continue;
+        }
         if (len64 > CH::MAX_LEN) {
             if (tid == 0) { a.status[idx] = BDF_STREAM_UNSUPPORTED; a.out_size[idx] = 0; }
             continue;
@@ -367,10 +371,10 @@ __global__ void __launch_bounds__(HC_THREADS) deflate_hc_kernel(DeflateArgs a)
         for (unsigned i = tid; i < 32768 * sizeof(typename CH::head_t) / 16; i += HC_THREADS)
             reinterpret_cast<uint4 *>(ch.head)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
         unsigned hdr = 0;
-        BitSink bs;
+        BitSinkT<SIZE> bs;
         if (warp == 0) {
-            hdr = frame_header(a.format, a.level, out, lane);
-            bs.init(sm.sink, out + hdr, unit_cap(len, uflags), lane);
+            hdr = SIZE ? 0 : frame_header(a.format, a.level, out, lane);
+            bs.init(sm.sink, SIZE ? nullptr : out + hdr, SIZE ? ~0ull : unit_cap(len, uflags), lane);
         }
         __syncthreads();
 
@@ -597,7 +601,7 @@ __global__ void __launch_bounds__(HC_THREADS) deflate_hc_kernel(DeflateArgs a)
             uint64_t sz = bs.finish(lane);
             int st = BDF_OK;
             if (sz == ~0ull) { st = BDF_INSUFFICIENT_SPACE; sz = 0; }
-            else sz = frame_footer(a.format, in, len, out, hdr + sz, sm.crc, sm.x2n, lane);
+            else if (!SIZE) sz = frame_footer(a.format, in, len, out, hdr + sz, sm.crc, sm.x2n, lane);
             if (lane == 0) { a.status[idx] = st; a.out_size[idx] = sz; }
         }
     }

@@ -70,7 +70,7 @@ __device__ __forceinline__ void static_off_code(unsigned off, uint32_t &bits, ui
     n = 5 + extra;
 }
 
-template <bool BIG>
+template <bool BIG, bool SIZE = false>
 __global__ void __launch_bounds__(L1_WARPS * 32) deflate_l1_kernel(DeflateArgs a)
 {
     using CFG = L1Cfg<BIG>;
@@ -89,18 +89,24 @@ __global__ void __launch_bounds__(L1_WARPS * 32) deflate_l1_kernel(DeflateArgs a
         if (idx >= a.n) break;
         const uint8_t *in = a.in + a.in_off[idx];
         const uint64_t len64 = a.in_off[idx + 1] - a.in_off[idx];
-        uint8_t *out = a.out + a.out_off[idx];
+        uint8_t *out = SIZE ? nullptr : a.out + a.out_off[idx];
+        if (SIZE && len64 == 0) {             // the estimator's block loop never runs (:808)
+            if (lane == 0) { a.status[idx] = BDF_OK; a.out_size[idx] = 0; }
+            continue;
+        }
         if (len64 > CFG::MAX_LEN) {
             if (lane == 0) { a.status[idx] = BDF_STREAM_UNSUPPORTED; a.out_size[idx] = 0; }
             continue;
         }
         const uint32_t len = (uint32_t)len64;
         const unsigned uflags = unit_flags_of(a, idx);
-        const bool split = BIG && len > 65536;       // :1505: at most 64 KiB is one block, no statistics
+        // :1505: at most 64 KiB is one block, no statistics; the size estimator always keeps them
+        // (accumulate_greedy_frequencies, :1096-1140)
+        const bool split = BIG && (len > 65536 || SIZE);
         for (unsigned i = lane; i < CFG::TABLE_BYTES / 16; i += 32) reinterpret_cast<uint4 *>(table)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
-        const unsigned hdr = frame_header(a.format, 1, out, lane);
-        BitSink bs;
-        bs.init(sm.sink[warp], out + hdr, unit_cap(len, uflags), lane);
+        const unsigned hdr = SIZE ? 0 : frame_header(a.format, 1, out, lane);
+        BitSinkT<SIZE> bs;
+        bs.init(sm.sink[warp], SIZE ? nullptr : out + hdr, SIZE ? ~0ull : unit_cap(len, uflags), lane);
         // BTYPE = 01; BFINAL of a block that may still be split is written as 0 and set at the end
         uint64_t bfinal_at = bs.bitpos();
         bs.put1((!split && (uflags & UNIT_FINISH) ? 1u : 0u) | 2u, 3, lane);
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(L1_WARPS * 32) deflate_l1_kernel(DeflateArgs a
         uint64_t sz = bs.finish(lane);
         int st_code = BDF_OK;
         if (sz == ~0ull) { st_code = BDF_INSUFFICIENT_SPACE; sz = 0; }
-        else sz = frame_footer(a.format, in, len, out, hdr + sz, sm.crc, sm.x2n, lane);
+        else if (!SIZE) sz = frame_footer(a.format, in, len, out, hdr + sz, sm.crc, sm.x2n, lane);
         if (lane == 0) { a.status[idx] = st_code; a.out_size[idx] = sz; }
         __syncwarp();
     }

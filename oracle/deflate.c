@@ -973,3 +973,5 @@ int orc_compress(int level, int format, const uint8_t *in, size_t in_len, uint8_
     *out_size = sz + 18;
     return ORC_OK;
 }
+
+#include "size.inc.c"

@@ -59,6 +59,10 @@ int orc_compress(int level, int format, const uint8_t *in, size_t in_len,
 int orc_compress_unit(int level, const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap,
                       int finish, int sync, size_t *out_size);
 
+/* Compressor::compress_to_size(input, final_block), src/compress/mod.rs:792-1094,1073-1094: the
+ * size estimate in bytes of raw DEFLATE (no framing); see size.inc.c. */
+size_t orc_compress_to_size(int level, const uint8_t *in, size_t in_len, int final_block);
+
 /* One stream.  in_consumed follows the reference (reader position, see
  * inflate.c header).  Returns an ORC_* status. */
 int orc_decompress(int format, const uint8_t *in, size_t in_len, uint8_t *out,

@@ -136,6 +136,21 @@ int main()
         auto out = d.decompress_batch({{sink.data.data(), sink.data.size()}}, {data.size()});
         CHECK(out[0].has_value() && *out[0] == data);
     }
+    // size estimation (Compressor::compress_to_size, src/compress/mod.rs:1073-1094): at the greedy /
+    // lazy levels the estimate is the length of the stream the compressor writes
+    {
+        std::vector<uint8_t> data(50000);
+        for (size_t i = 0; i < data.size(); i++) data[i] = (uint8_t)((i * 13 + i / 700) % 241);
+        bdf::BatchCompressor c6(6, BDF_RAW, ctx);
+        auto est = c6.compress_to_size_batch({{data.data(), data.size()}, {data.data(), 0}});
+        auto comp = c6.compress_batch({{data.data(), data.size()}});
+        CHECK(est[0] == comp[0].size());
+        CHECK(est[1] == 0);
+        bdf::BatchCompressor c0(0, BDF_RAW, ctx);
+        CHECK(c0.compress_to_size_batch({{data.data(), 0}}, true)[0] == 5);
+        CHECK(c0.compress_to_size_batch({{data.data(), 0}}, false)[0] == 0);
+        CHECK(c0.compress_to_size_batch({{data.data(), data.size()}})[0] == data.size() + 5);
+    }
     std::puts("batch_test.cpp: all reference batch tests passed");
     return 0;
 }

@@ -44,6 +44,8 @@ def lib():
         L.orc_compress_unit.restype = C.c_int
         L.orc_compress_unit.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                         C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+        L.orc_compress_to_size.restype = C.c_size_t
+        L.orc_compress_to_size.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.c_int]
         L.orc_decompress.restype = C.c_int
         L.orc_decompress.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                      C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
@@ -91,6 +93,12 @@ def compress_unit(data, level, finish, sync, cap=None):
     sz = C.c_size_t(0)
     st = lib().orc_compress_unit(level, data, len(data), out, cap, int(finish), int(sync), C.byref(sz))
     return out.raw[:sz.value] if st == OK else None
+
+
+def compress_to_size(data, level, final_block=True):
+    """Compressor::compress_to_size (src/compress/mod.rs:1073-1094): estimated raw DEFLATE bytes."""
+    data = bytes(data)
+    return lib().orc_compress_to_size(level, data, len(data), int(final_block))
 
 
 def decompress(data, max_out, fmt=RAW, full=False):

@@ -219,3 +219,31 @@ def test_chunked_and_unit_streams_are_valid_deflate():
         stream = b"".join(o.compress_unit(p, level, i == len(parts) - 1, i != len(parts) - 1)
                           for i, p in enumerate(parts))
         assert zlib.decompress(stream, -15) == b"".join(parts)
+
+
+def test_compress_to_size_restatement():
+    """orc_compress_to_size (Compressor::compress_to_size, src/compress/mod.rs:792-1094): at levels
+    2..9 the estimator parses like the compressor, so it must equal the emitted raw length; level 0
+    is the closed form of :1073-1082; level 1 can only add whole static-block headers (10 bits
+    each) over the single-block stream; an empty input costs nothing above level 0."""
+    import corpus
+    bufs = [corpus.text_stream(1, 65536), corpus.binary_stream(2, 65536)[:30011], corpus.lowentropy_stream(3, 65536),
+            corpus.periodic_stream(4, 65536)[:777], corpus.corpus_a_stream(1), (corpus.text_stream(5, 65536) * 3)[:150000],
+            b"a", b"abc" * 5]
+    for level in range(2, 10):
+        for b in bufs:
+            c = o.compress(b, level)
+            if c is not None:
+                assert o.compress_to_size(b, level) == len(c), (level, len(b))
+    for b in bufs:
+        n = len(b)
+        assert o.compress_to_size(b, 0) == n + 5 * (n // 65535 + (1 if n % 65535 else 0))
+        c = o.compress(b, 1)
+        est = o.compress_to_size(b, 1)
+        assert len(c) <= est <= len(c) + 2 + (10 * (n // 5000 + 1) + 7) // 8, (n, est, len(c))
+        for level in (10, 12):
+            if n <= 70000:
+                c = o.compress(b, level)
+                assert abs(o.compress_to_size(b, level) - len(c)) <= max(8, len(c) // 100), (level, n)
+    assert o.compress_to_size(b"", 0, True) == 5 and o.compress_to_size(b"", 0, False) == 0
+    assert [o.compress_to_size(b"", lv) for lv in (1, 6, 12)] == [0, 0, 0]
