@@ -77,7 +77,10 @@ uint64_t bdf_kernel_launches(const bdf_ctx *ctx);
 float bdf_last_kernel_ms(const bdf_ctx *ctx);
 
 /* Pinned host memory for the *_host entry points (pageable memory also works,
- * through the driver's staging copies). */
+ * through the driver's staging copies).  The pages are placed on the NUMA node
+ * of the calling thread's current CUDA device (the thread's CPU affinity is
+ * narrowed to that node for the duration of the call; BDF_HOST_ALLOC_NUMA=0
+ * disables it): call it after cudaSetDevice / bdf_ctx_create for that GPU. */
 void *bdf_host_alloc(size_t bytes);
 void bdf_host_free(void *p);
 

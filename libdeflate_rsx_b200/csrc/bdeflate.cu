@@ -5,6 +5,8 @@
 // There is no CPU path here: every entry point either runs the CUDA kernels or
 // returns a negative bdf_error.
 #include <cuda_runtime.h>
+#include <ctype.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -199,11 +201,69 @@ const char *bdf_last_error(const bdf_ctx *ctx) { return ctx ? ctx->err : "null c
 uint64_t bdf_kernel_launches(const bdf_ctx *ctx) { return ctx ? ctx->launches : 0; }
 float bdf_last_kernel_ms(const bdf_ctx *ctx) { return ctx ? ctx->last_ms : 0.f; }
 
+// NUMA node of the calling thread's current CUDA device (sysfs), -1 if unknown
+static int current_device_numa_node()
+{
+    int dev = 0;
+    char bus[64];
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), dev) != cudaSuccess)
+        return -1;
+    for (char *c = bus; *c; c++) *c = (char)tolower((unsigned char)*c);
+    char path[160];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+// CPUs of a NUMA node ("0-55,112-167"); false if the list cannot be read
+static bool numa_node_cpus(int node, cpu_set_t *set)
+{
+    char path[96];
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    FILE *f = fopen(path, "r");
+    if (!f) return false;
+    CPU_ZERO(set);
+    int a = 0, b = 0, any = 0;
+    for (;;) {
+        if (fscanf(f, "%d", &a) != 1) break;
+        b = a;
+        int c = fgetc(f);
+        if (c == '-') {
+            if (fscanf(f, "%d", &b) != 1) break;
+            c = fgetc(f);
+        }
+        for (int k = a; k <= b && k < CPU_SETSIZE; k++) { CPU_SET(k, set); any = 1; }
+        if (c != ',') break;
+    }
+    fclose(f);
+    return any != 0;
+}
+
+// Pinned memory is placed by first touch, i.e. on the NUMA node of the thread inside cudaHostAlloc.
+// On a two-socket 8-GPU box a result slab on the far socket crosses the inter-socket link together
+// with the slabs of the other GPUs, so the calling thread is moved next to its current CUDA device
+// for the duration of the allocation.  BDF_HOST_ALLOC_NUMA=0 switches this off.  (The B200 pool this
+// was developed on is virtualised: one NUMA node, numa_node = -1 for every GPU, so the call changes
+// nothing there — 8 ranks returning 4 GiB each reach 91-93 GB/s in total with or without it.)
 void *bdf_host_alloc(size_t bytes)
 {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
-    return p;
+    cpu_set_t old_set, node_set, want;
+    bool moved = false;
+    const char *env = getenv("BDF_HOST_ALLOC_NUMA");
+    if (!(env && atoi(env) == 0) && sched_getaffinity(0, sizeof(old_set), &old_set) == 0) {
+        const int node = current_device_numa_node();
+        if (node >= 0 && numa_node_cpus(node, &node_set)) {
+            CPU_AND(&want, &old_set, &node_set);
+            if (CPU_COUNT(&want) > 0 && sched_setaffinity(0, sizeof(want), &want) == 0) moved = true;
+        }
+    }
+    const cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (moved) sched_setaffinity(0, sizeof(old_set), &old_set);
+    return e == cudaSuccess ? p : nullptr;
 }
 void bdf_host_free(void *p)
 {
