@@ -3,6 +3,8 @@
 // each written front to back.  mode 0: 16 lanes x STG.128; mode 1: one lane issues cp.async.bulk
 // shared -> global copies of `piece` bytes (the replay of inflate.cuh); mode 2: plain grid-stride
 // fill (every warp writes consecutive 512-byte rows).  Prints GB/s per mode.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o gpurun_scripts/probe/write_probe gpurun_scripts/probe/write_probe.cu
+// run:   gpurun -- 'gpurun_scripts/probe/write_probe 65536'
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
