@@ -102,6 +102,11 @@ class ShardedBatch:
         from .batch import BatchCompressor
         return self._run(inputs, lambda ctx, lo, hi: BatchCompressor(level, format, ctx).compress_batch(inputs[lo:hi]))
 
+    def compress_to_size_batch(self, inputs, level, final_block=True):
+        from .batch import BatchCompressor
+        return self._run(inputs, lambda ctx, lo, hi: BatchCompressor(level, 0, ctx).compress_to_size_batch(
+            inputs[lo:hi], final_block))
+
     def decompress_batch(self, inputs, max_out_sizes, format=0):
         from .batch import BatchDecompressor
         n = min(len(inputs), len(max_out_sizes))

@@ -247,3 +247,26 @@ def test_compress_to_size_restatement():
                 assert abs(o.compress_to_size(b, level) - len(c)) <= max(8, len(c) // 100), (level, n)
     assert o.compress_to_size(b"", 0, True) == 5 and o.compress_to_size(b"", 0, False) == 0
     assert [o.compress_to_size(b"", lv) for lv in (1, 6, 12)] == [0, 0, 0]
+
+
+def test_compress_to_size_random_buffers():
+    """Seeded ragged buffers: at levels 2..9 the estimator's byte count is the length of the raw
+    stream the compressor writes whenever that stream fits the bound; the stream itself inflates
+    under system zlib."""
+    import zlib
+    import corpus
+    rng = np.random.default_rng(23)
+    gens = (corpus.text_stream, corpus.binary_stream, corpus.lowentropy_stream, corpus.periodic_stream)
+    for trial in range(40):
+        n = int(rng.integers(0, 70000)) if trial % 5 else int(rng.integers(0, 40))
+        base = gens[trial % 4](int(rng.integers(0, 1000)), 65536)
+        start = int(rng.integers(0, 2000))
+        b = (base * 2)[start:start + n]
+        level = int(rng.integers(2, 10))
+        c = o.compress(b, level)
+        est = o.compress_to_size(b, level)
+        if len(b) == 0:
+            assert est == 0
+        elif c is not None:
+            assert est == len(c), (trial, level, len(b))
+            assert zlib.decompress(c, -15) == b

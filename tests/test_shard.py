@@ -97,6 +97,9 @@ def test_sharded_batch_orders_results_without_a_gpu():
             calls.append((self.ctx.device, len(bufs)))
             return [o.compress(b, self.level, self.format) or b"" for b in bufs]
 
+        def compress_to_size_batch(self, bufs, final_block=True):
+            return [o.compress_to_size(b, self.level, final_block) for b in bufs]
+
     real = batch.BatchCompressor
     batch.BatchCompressor = FakeCompressor
     try:
@@ -106,5 +109,6 @@ def test_sharded_batch_orders_results_without_a_gpu():
         assert got == [o.compress(b, 6, 1) for b in bufs]
         assert sorted(d for d, _ in calls) == [0, 1, 2] and sum(c for _, c in calls) == len(bufs)
         assert sb.compress_batch([], 6) == []
+        assert sb.compress_to_size_batch(bufs, 6) == [o.compress_to_size(b, 6) for b in bufs]
     finally:
         batch.BatchCompressor = real
