@@ -270,3 +270,19 @@ def test_compress_to_size_random_buffers():
         elif c is not None:
             assert est == len(c), (trial, level, len(b))
             assert zlib.decompress(c, -15) == b
+
+
+def test_bit_writer_capacity_boundary():
+    """tests/bitstream_boundary.rs: a write that ends exactly at the end of the buffer succeeds.
+    Through the compressor: a chunk fits a buffer of exactly its compressed size and fails in one
+    byte less (Bitstream's checked writes, src/compress/bitstream.rs:143-222), at every level and
+    for both flush modes."""
+    import corpus
+    bufs = [corpus.text_stream(3, 65536)[:5000], corpus.binary_stream(4, 65536)[:777], b"ab" * 40, b"x"]
+    for level in (0, 1, 4, 6, 9, 10):
+        for b in bufs:
+            for finish, sync in ((True, False), (False, True)):
+                full = o.compress_unit(b, level, finish, sync)
+                assert full is not None
+                assert o.compress_unit(b, level, finish, sync, cap=len(full)) == full
+                assert o.compress_unit(b, level, finish, sync, cap=len(full) - 1) is None
