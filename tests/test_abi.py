@@ -80,3 +80,8 @@ def test_safe_api_guards_need_no_gpu():
     d.set_limit_ratio(10)
     with pytest.raises(ValueError, match="safety limit"):
         d.decompress_gzip_batch([bytes(10), bytes(10)], [4000, 5000])   # second stream: 5000 > 4196
+    # tests/security_oom.rs: an 8 GiB request backed by 5 MiB of input passes the ratio guard and must
+    # end in an ordinary error, never a crash (here: no GPU, so the engine refuses to start)
+    if not __import__("torch").cuda.is_available():
+        with pytest.raises(bdf.BdfError):
+            bdf.Decompressor().decompress_deflate(bytes(5 << 20), 8 << 30)

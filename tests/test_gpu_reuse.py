@@ -63,3 +63,13 @@ def test_encoder_one_mebibyte_of_zeros(engine):
     out = sink.getvalue()
     assert len(out) > 0
     assert zlib.decompress(out, -15) == data
+
+
+def test_huge_expected_size_small_stream(engine):
+    """tests/security_oom.rs scaled to 1 GiB: a tiny valid stream at the head of a large input slice,
+    a huge expected size that passes the ratio guard — the call returns the 100 bytes (or an
+    ordinary error), it does not crash."""
+    comp = engine.Compressor(1).compress_deflate(b"A" * 100)
+    big = comp + bytes(600 * 1024 - len(comp))
+    got = engine.Decompressor().decompress_deflate(big, 1 << 30)
+    assert got == b"A" * 100
