@@ -156,9 +156,13 @@ class BatchDecompressor:
 
     def decompress_flat(self, flat, in_off, max_out, want_checksum=False):
         n = len(in_off) - 1
-        max_out = np.ascontiguousarray(max_out, dtype=np.uint64)
+        caps = [int(v) for v in max_out]
+        total = sum(caps)                   # Python ints: a uint64 sum would wrap silently
+        if any(v < 0 for v in caps) or total >= 1 << 46:
+            raise N.BdfError("decompress_batch: output capacities add up to %d bytes" % total)
+        max_out = np.array(caps, dtype=np.uint64)
         out_off = exclusive_offsets(max_out)
-        out = np.empty(max(int(max_out.sum()), 1), dtype=np.uint8)
+        out = np.empty(max(total, 1), dtype=np.uint8)
         out_size = np.zeros(n, dtype=np.uint64)
         status = np.zeros(n, dtype=np.int32)
         checksum = np.zeros(n, dtype=np.uint32)

@@ -18,9 +18,14 @@
 #include "../../include/bdeflate.h"
 #include "checksum.cuh"
 #include "inflate.cuh"
+#include "inflate_lane.cuh"
 #include "deflate.cuh"
 
 namespace {
+
+// staging slabs are sized from caller-supplied offsets: refuse anything above 2^46 bytes outright
+// (far above any GPU's memory) so that sums cannot wrap
+constexpr uint64_t BDF_MAX_SLAB_BYTES = 1ull << 46;
 
 struct DevBuf {
     void *p = nullptr;
@@ -35,6 +40,15 @@ struct bdf_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t copy_streams[8] = {};          // large device-to-host results go out as 8 concurrent copies
+    int d2h_streams = 8;                        // how many of them a call uses (BDF_D2H_STREAMS; fewer when many ranks share the host)
+    unsigned copy_waited = 0;
+    cudaStream_t aux_stream = nullptr;          // second engine of a decompress call (runs beside the first)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // Launches that use ctx-owned device scratch (compressor slabs, work-queue heads) are ordered
+    // one after the other even when the callers pass different CUDA streams: every such launch
+    // waits for ev_order of the previous one and records it again.
+    cudaEvent_t ev_order = nullptr;
+    bool order_pending = false;
     std::mutex mu;
     char err[320] = {0};
     uint64_t launches = 0;
@@ -42,7 +56,11 @@ struct bdf_ctx {
     unsigned long long *d_counters = nullptr;   // work-queue heads, one slot per launch in flight
     unsigned counter_slot = 0;
     int inflate_blocks_per_sm[3] = {0, 0, 0};
+    int lane_blocks_per_sm[3] = {0, 0, 0};
     int inflate_group = 16;                     // lanes per stream in inflate_kernel (BDF_INFLATE_GROUP)
+    int inflate_mode = 0;                       // 0 = both engines, split by expansion ratio; 1 = lane groups only; 2 = lane per stream only (BDF_INFLATE_MODE)
+    int inflate_split = 16;                     // expansion ratio from which a stream goes to the lane-group kernel (BDF_INFLATE_SPLIT)
+    int lane_cfg = 0;                           // 0: 9-bit table, 1 KiB ring (2 warps / SM); 1: 8-bit table, 512 B ring (3 warps / SM) (BDF_LANE_CFG)
     bdf::DeflateScratch deflate_scratch;
     DevBuf in, out, in_off, out_off, max_out, out_size, status, checksum;
     DevBuf u_in_off, u_tmp_off, u_size, u_status, u_flags, u_begin, u_tmp;     // chunked compression (units)
@@ -50,7 +68,10 @@ struct bdf_ctx {
 
 namespace {
 
-constexpr unsigned NUM_COUNTER_SLOTS = 64;
+// Work-queue heads: one slot per launch, handed out round robin.  A slot is reused after
+// NUM_COUNTER_SLOTS further launches; launches through one ctx are ordered (ev_order), so the
+// earlier user of a slot has finished long before.
+constexpr unsigned NUM_COUNTER_SLOTS = 1024;
 
 int fail(bdf_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
 {
@@ -86,8 +107,21 @@ int ensure(bdf_ctx *ctx, DevBuf &b, size_t bytes)
 unsigned long long *next_counter(bdf_ctx *ctx, cudaStream_t s)
 {
     unsigned long long *c = ctx->d_counters + (ctx->counter_slot++ % NUM_COUNTER_SLOTS);
-    cudaMemsetAsync(c, 0, sizeof(*c), s);
+    if (cudaMemsetAsync(c, 0, sizeof(*c), s) != cudaSuccess) return nullptr;
     return c;
+}
+
+// see bdf_ctx::ev_order
+int order_begin(bdf_ctx *ctx, cudaStream_t s)
+{
+    if (ctx->order_pending) CK(cudaStreamWaitEvent(s, ctx->ev_order, 0));
+    return 0;
+}
+int order_end(bdf_ctx *ctx, cudaStream_t s)
+{
+    CK(cudaEventRecord(ctx->ev_order, s));
+    ctx->order_pending = true;
+    return 0;
 }
 
 template <int FORMAT, int G>
@@ -111,13 +145,63 @@ int launch_inflate_g(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
     return 0;
 }
 
+template <int FORMAT, int LTB, int RING>
+int launch_inflate_lane_c(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
+{
+    const size_t smem = sizeof(bdf::LaneSmem<LTB, RING>);
+    int &bps = ctx->lane_blocks_per_sm[FORMAT];
+    if (bps == 0) {
+        CK(cudaFuncSetAttribute(bdf::inflate_lane_kernel<FORMAT, LTB, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(bdf::inflate_lane_kernel<FORMAT, LTB, RING>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, bdf::inflate_lane_kernel<FORMAT, LTB, RING>, 32, smem));
+        if (bps < 1) bps = 1;
+    }
+    unsigned long long want = ((unsigned long long)a.n + 31) / 32;
+    unsigned long long full = (unsigned long long)ctx->sm_count * bps;
+    unsigned grid = (unsigned)(want < full ? want : full);
+    bdf::inflate_lane_kernel<FORMAT, LTB, RING><<<grid, 32, smem, s>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 template <int FORMAT>
-int launch_inflate(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
+int launch_inflate_lane(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
+{
+    if (ctx->lane_cfg == 1) return launch_inflate_lane_c<FORMAT, 8, 512>(ctx, a, s);
+    return launch_inflate_lane_c<FORMAT, 9, 1024>(ctx, a, s);
+}
+
+template <int FORMAT>
+int launch_inflate_group(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
 {
     switch (ctx->inflate_group) {
         case 32: return launch_inflate_g<FORMAT, 32>(ctx, a, s);
         default: return launch_inflate_g<FORMAT, 16>(ctx, a, s);
     }
+}
+
+// Both engines of a decompress call: the lane-group kernel on the caller's stream, the
+// lane-per-stream kernel beside it on the ctx's aux stream (fork / join with events), each
+// taking the streams of its class.  classes: bit 0 = heavy streams present, bit 1 = light ones
+// (3 when the caller cannot tell, i.e. the offsets live on the device).
+template <int FORMAT>
+int launch_inflate(bdf_ctx *ctx, bdf::InflateArgs a, cudaStream_t s, int classes)
+{
+    if (ctx->inflate_mode == 1) { a.split_ratio = 0; return launch_inflate_group<FORMAT>(ctx, a, s); }
+    if (ctx->inflate_mode == 2) { a.split_ratio = 0; return launch_inflate_lane<FORMAT>(ctx, a, s); }
+    a.split_ratio = (uint32_t)ctx->inflate_split;
+    if (classes == 1) return launch_inflate_group<FORMAT>(ctx, a, s);
+    if (classes == 2) return launch_inflate_lane<FORMAT>(ctx, a, s);
+    CK(cudaEventRecord(ctx->ev_fork, s));
+    CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    int rc = launch_inflate_lane<FORMAT>(ctx, a, ctx->aux_stream);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    rc = launch_inflate_group<FORMAT>(ctx, a, s);
+    if (rc) return rc;
+    CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+    return 0;
 }
 
 bool bad_format(int f) { return f != BDF_RAW && f != BDF_ZLIB && f != BDF_GZIP; }
@@ -156,12 +240,38 @@ int bdf_ctx_create(int device, bdf_ctx **out)
         int v = atoi(e);
         if (v == 16 || v == 32) ctx->inflate_group = v;
     }
+    if (const char *e = getenv("BDF_INFLATE_MODE")) {
+        if (!strcmp(e, "group")) ctx->inflate_mode = 1;
+        else if (!strcmp(e, "lane")) ctx->inflate_mode = 2;
+    }
+    if (const char *e = getenv("BDF_INFLATE_SPLIT")) {
+        int v = atoi(e);
+        if (v >= 1 && v <= 1032) ctx->inflate_split = v;
+    }
+    if (const char *e = getenv("BDF_LANE_CFG")) ctx->lane_cfg = atoi(e) == 1 ? 1 : 0;
+    {
+        // Device-to-host result copies per call.  Eight concurrent copies are best when one process
+        // owns the host (56.6 vs 51 GB/s); with several ranks returning results to the same host at once
+        // the copies of all ranks share its memory system, so each rank uses fewer (LOCAL_WORLD_SIZE is
+        // set by torchrun).  BDF_D2H_STREAMS overrides.
+        int ranks = 1;
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e) > 0 ? atoi(e) : 1;
+        ctx->d2h_streams = ranks >= 8 ? 2 : ranks >= 4 ? 2 : ranks >= 2 ? 4 : 8;
+        if (const char *e = getenv("BDF_D2H_STREAMS")) {
+            int v = atoi(e);
+            if (v >= 1 && v <= 8) ctx->d2h_streams = v;
+        }
+    }
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&ctx->copy_streams[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counters, NUM_COUNTER_SLOTS * sizeof(unsigned long long));
     if (e == cudaSuccess) {
         bdf::crc_tables_init_kernel<<<1, 256, 0, ctx->stream>>>();
@@ -191,8 +301,12 @@ void bdf_ctx_destroy(bdf_ctx *ctx)
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     for (int i = 0; i < 8; i++)
         if (ctx->copy_streams[i]) cudaStreamDestroy(ctx->copy_streams[i]);
+    if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -276,22 +390,46 @@ size_t bdf_compress_bound(int format, size_t len)
     return b + (format == BDF_ZLIB ? 6 : format == BDF_GZIP ? 18 : 0);
 }
 
+// One ordered launch of the compression kernels (they all work in ctx->deflate_scratch).
+static int run_deflate(bdf_ctx *ctx, bdf::DeflateArgs &a, cudaStream_t s, uint64_t max_len)
+{
+    int rc = order_begin(ctx, s);
+    if (rc) return rc;
+    a.work_counter = next_counter(ctx, s);
+    if (!a.work_counter) return fail(ctx, BDF_E_CUDA, "cudaMemsetAsync(work counter)");
+    int nl = 0;
+    const char *why = nullptr;
+    cudaError_t e = bdf::launch_deflate(a, ctx->deflate_scratch, ctx->sm_count, s, &nl, &why, max_len);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail(ctx, BDF_E_CUDA, why ? why : "launch_deflate", e);
+    if (why) return fail(ctx, BDF_E_UNSUPPORTED, why);
+    return order_end(ctx, s);
+}
+
 // ---------------------------------------------------------------- decompress
 static int decompress_device_locked(bdf_ctx *ctx, int format, const uint8_t *in, const uint64_t *in_off,
                                     size_t n, uint8_t *out, const uint64_t *out_off, const uint64_t *max_out,
-                                    uint64_t *out_size, uint32_t *checksum, int32_t *status, cudaStream_t s)
+                                    uint64_t *out_size, uint32_t *checksum, int32_t *status, cudaStream_t s,
+                                    int classes = 3)
 {
     if (n == 0) return BDF_E_OK;
     if (n > 0xFFFFFFF0ull) return fail(ctx, BDF_E_ARG, "too many streams");
+    int rc = order_begin(ctx, s);
+    if (rc) return rc;
     bdf::InflateArgs a;
     a.in = in; a.in_off = in_off; a.out = out; a.out_off = out_off; a.max_out = max_out;
     a.out_size = out_size; a.checksum = checksum; a.status = status; a.n = (uint32_t)n;
+    a.split_ratio = 0;
     a.work_counter = next_counter(ctx, s);
+    a.work_counter2 = next_counter(ctx, s);
+    if (!a.work_counter || !a.work_counter2) return fail(ctx, BDF_E_CUDA, "cudaMemsetAsync(work counter)");
     switch (format) {
-        case BDF_RAW: return launch_inflate<BDF_RAW>(ctx, a, s);
-        case BDF_ZLIB: return launch_inflate<BDF_ZLIB>(ctx, a, s);
-        default: return launch_inflate<BDF_GZIP>(ctx, a, s);
+        case BDF_RAW: rc = launch_inflate<BDF_RAW>(ctx, a, s, classes); break;
+        case BDF_ZLIB: rc = launch_inflate<BDF_ZLIB>(ctx, a, s, classes); break;
+        default: rc = launch_inflate<BDF_GZIP>(ctx, a, s, classes); break;
     }
+    if (rc) return rc;
+    return order_end(ctx, s);
 }
 
 int bdf_decompress_batch_device(bdf_ctx *ctx, int format, const uint8_t *in, const uint64_t *in_off, size_t n,
@@ -309,6 +447,31 @@ int bdf_decompress_batch_device(bdf_ctx *ctx, int format, const uint8_t *in, con
                                     status, s);
 }
 
+// Copies [beg, end) of a device slab to the same offsets of a host buffer.  Large ranges go out as
+// several concurrent copies (one copy engine stream does not saturate the link: 51 GB/s with one
+// copy of 4 GiB on the development box, 56.6 GB/s with eight); `after` has been recorded on the
+// stream that produced the data.
+static int copy_range_d2h(bdf_ctx *ctx, uint8_t *host, const uint8_t *dev, size_t beg, size_t end, cudaEvent_t after,
+                          int *next_stream)
+{
+    const size_t bytes = end - beg;
+    const int nstreams = ctx->d2h_streams;
+    int pieces = 1;
+    if (bytes >= (64u << 20)) pieces = nstreams;
+    const size_t piece = ((bytes + pieces - 1) / pieces + ((1u << 20) - 1)) & ~(size_t)((1u << 20) - 1);
+    for (size_t o = 0; o < bytes; o += piece) {
+        const size_t cnt = bytes - o < piece ? bytes - o : piece;
+        cudaStream_t cs = ctx->copy_streams[*next_stream % nstreams];
+        if (!(ctx->copy_waited >> (*next_stream % nstreams) & 1u)) {
+            CK(cudaStreamWaitEvent(cs, after, 0));
+            ctx->copy_waited |= 1u << (*next_stream % nstreams);
+        }
+        CK(cudaMemcpyAsync(host + beg + o, dev + beg + o, cnt, cudaMemcpyDeviceToHost, cs));
+        (*next_stream)++;
+    }
+    return 0;
+}
+
 int bdf_decompress_batch_host(bdf_ctx *ctx, int format, const uint8_t *in, const uint64_t *in_off, size_t n,
                               uint8_t *out, const uint64_t *out_off, const uint64_t *max_out,
                               uint64_t *out_size, uint32_t *checksum, int32_t *status)
@@ -323,9 +486,16 @@ int bdf_decompress_batch_host(bdf_ctx *ctx, int format, const uint8_t *in, const
     cudaStream_t s = ctx->stream;
     const size_t in_bytes = (size_t)in_off[n];
     size_t out_bytes = 0;
+    int classes = 0;
+    const uint64_t split = (uint64_t)ctx->inflate_split;
     for (size_t i = 0; i < n; i++) {
-        size_t e = (size_t)(out_off[i] + max_out[i]);
-        if (e > out_bytes) out_bytes = e;
+        // the slab is sized from these sums: a wrapped sum would let the kernel write past it
+        if (in_off[i] > in_off[i + 1] || in_off[i + 1] > in_off[n]) return fail(ctx, BDF_E_ARG, "in_off is not ascending");
+        const uint64_t e = out_off[i] + max_out[i];
+        if (e < out_off[i] || e > BDF_MAX_SLAB_BYTES) return fail(ctx, BDF_E_ARG, "out_off + max_out overflows");
+        if (e > out_bytes) out_bytes = (size_t)e;
+        const uint64_t len = in_off[i + 1] - in_off[i];
+        classes |= max_out[i] >= split * (len ? len : 1) ? 1 : 2;
     }
     if (overlaps(in, in_bytes, out, out_bytes)) return fail(ctx, BDF_E_ARG, "Input and output buffers overlap");
     int rc;
@@ -342,29 +512,32 @@ int bdf_decompress_batch_host(bdf_ctx *ctx, int format, const uint8_t *in, const
     rc = decompress_device_locked(ctx, format, (const uint8_t *)ctx->in.p, (const uint64_t *)ctx->in_off.p, n,
                                   (uint8_t *)ctx->out.p, (const uint64_t *)ctx->out_off.p,
                                   (const uint64_t *)ctx->max_out.p, (uint64_t *)ctx->out_size.p,
-                                  (uint32_t *)ctx->checksum.p, (int32_t *)ctx->status.p, s);
+                                  (uint32_t *)ctx->checksum.p, (int32_t *)ctx->status.p, s, classes);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, s));
     CK(cudaMemcpyAsync(out_size, ctx->out_size.p, n * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(status, ctx->status.p, n * 4, cudaMemcpyDeviceToHost, s));
     if (checksum) CK(cudaMemcpyAsync(checksum, ctx->checksum.p, n * 4, cudaMemcpyDeviceToHost, s));
-    if (out_bytes >= (64u << 20)) {
-        // One copy engine stream does not saturate the link (measured on this box: 51 GB/s with one
-        // copy of 4 GiB, 56.6 GB/s with eight concurrent ones): the slab goes out in 8 pieces.
-        const size_t piece = ((out_bytes + 7) / 8 + ((1u << 20) - 1)) & ~(size_t)((1u << 20) - 1);
-        for (int i = 0; i < 8; i++) {
-            const size_t beg = (size_t)i * piece;
-            if (beg >= out_bytes) break;
-            const size_t cnt = out_bytes - beg < piece ? out_bytes - beg : piece;
-            CK(cudaStreamWaitEvent(ctx->copy_streams[i], ctx->ev1, 0));
-            CK(cudaMemcpyAsync(out + beg, (const uint8_t *)ctx->out.p + beg, cnt, cudaMemcpyDeviceToHost,
-                               ctx->copy_streams[i]));
-        }
-        for (int i = 0; i < 8; i++) CK(cudaStreamSynchronize(ctx->copy_streams[i]));
-    } else if (out_bytes) {
-        CK(cudaMemcpyAsync(out, ctx->out.p, out_bytes, cudaMemcpyDeviceToHost, s));
-    }
     CK(cudaStreamSynchronize(s));
+    // Only what the streams produced comes back: [out_off[i], out_off[i] + out_size[i]) of every
+    // stream, neighbours that touch merged into one range.  Nothing outside a slot is written, the
+    // rest of a slot (and the whole slot of a failed stream) keeps the caller's bytes.
+    ctx->copy_waited = 0;
+    int next_stream = 0;
+    size_t i = 0;
+    while (i < n) {
+        size_t beg = (size_t)out_off[i], end = beg + (size_t)out_size[i];
+        size_t j = i + 1;
+        while (j < n && (size_t)out_off[j] == end) {
+            end += (size_t)out_size[j];
+            j++;
+        }
+        if (end > beg && (rc = copy_range_d2h(ctx, out, (const uint8_t *)ctx->out.p, beg, end, ctx->ev1, &next_stream)))
+            return rc;
+        i = j;
+    }
+    for (int k = 0; k < ctx->d2h_streams; k++)
+        if (ctx->copy_waited >> k & 1u) CK(cudaStreamSynchronize(ctx->copy_streams[k]));
     cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
     return BDF_E_OK;
 }
@@ -377,14 +550,7 @@ static int compress_device_locked(bdf_ctx *ctx, int level, int format, const uin
     bdf::DeflateArgs a;
     a.in = in; a.in_off = in_off; a.out = out; a.out_off = out_off; a.out_size = out_size; a.status = status;
     a.n = (uint32_t)n; a.level = level > 12 ? 12 : level; a.format = format; a.unit_flags = nullptr;
-    a.work_counter = next_counter(ctx, s);
-    int nl = 0;
-    const char *why = nullptr;
-    cudaError_t e = bdf::launch_deflate(a, ctx->deflate_scratch, ctx->sm_count, s, &nl, &why);
-    ctx->launches += nl;
-    if (e != cudaSuccess) return fail(ctx, BDF_E_CUDA, why ? why : "launch_deflate", e);
-    if (why) return fail(ctx, BDF_E_UNSUPPORTED, why);
-    return BDF_E_OK;
+    return run_deflate(ctx, a, s, 0);
 }
 
 int bdf_compress_batch_device(bdf_ctx *ctx, int level, int format, const uint8_t *in, const uint64_t *in_off,
@@ -451,13 +617,7 @@ static int compress_chunked_locked(bdf_ctx *ctx, int level, int format, const ui
     a.out_size = (uint64_t *)ctx->u_size.p; a.status = (int32_t *)ctx->u_status.p;
     a.n = (uint32_t)nu; a.level = level > 12 ? 12 : level; a.format = BDF_RAW;
     a.unit_flags = (const uint8_t *)ctx->u_flags.p;
-    a.work_counter = next_counter(ctx, s);
-    int nl = 0;
-    const char *why = nullptr;
-    cudaError_t e = bdf::launch_deflate(a, ctx->deflate_scratch, ctx->sm_count, s, &nl, &why, max_unit);
-    ctx->launches += nl;
-    if (e != cudaSuccess) return fail(ctx, BDF_E_CUDA, why ? why : "launch_deflate", e);
-    if (why) return fail(ctx, BDF_E_UNSUPPORTED, why);
+    if ((rc = run_deflate(ctx, a, s, max_unit))) return rc;
     bdf::JoinArgs j;
     j.in = (const uint8_t *)ctx->in.p; j.in_off = (const uint64_t *)ctx->in_off.p;
     j.unit_begin = (const uint32_t *)ctx->u_begin.p; j.tmp = (const uint8_t *)ctx->u_tmp.p;
@@ -592,13 +752,7 @@ int bdf_compress_units_host(bdf_ctx *ctx, int level, const uint8_t *in, const ui
     a.out_size = (uint64_t *)ctx->out_size.p; a.status = (int32_t *)ctx->status.p;
     a.n = (uint32_t)n; a.level = level > 12 ? 12 : level; a.format = BDF_RAW;
     a.unit_flags = (const uint8_t *)ctx->u_flags.p;
-    a.work_counter = next_counter(ctx, s);
-    int nl = 0;
-    const char *why = nullptr;
-    cudaError_t e = bdf::launch_deflate(a, ctx->deflate_scratch, ctx->sm_count, s, &nl, &why, max_unit);
-    ctx->launches += nl;
-    if (e != cudaSuccess) return fail(ctx, BDF_E_CUDA, why ? why : "launch_deflate", e);
-    if (why) return fail(ctx, BDF_E_UNSUPPORTED, why);
+    if ((rc = run_deflate(ctx, a, s, max_unit))) return rc;
     CK(cudaEventRecord(ctx->ev1, s));
     CK(cudaMemcpyAsync(out_size, ctx->out_size.p, n * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(status, ctx->status.p, n * 4, cudaMemcpyDeviceToHost, s));
@@ -621,14 +775,7 @@ static int compress_size_locked(bdf_ctx *ctx, int level, const uint8_t *in, cons
     a.in = in; a.in_off = in_off; a.out = nullptr; a.out_off = nullptr; a.out_size = out_size; a.status = status;
     a.n = (uint32_t)n; a.level = level > 12 ? 12 : level; a.format = BDF_RAW; a.unit_flags = nullptr;
     a.size_only = 1; a.final_block = final_block ? 1 : 0;
-    a.work_counter = next_counter(ctx, s);
-    int nl = 0;
-    const char *why = nullptr;
-    cudaError_t e = bdf::launch_deflate(a, ctx->deflate_scratch, ctx->sm_count, s, &nl, &why, max_len);
-    ctx->launches += nl;
-    if (e != cudaSuccess) return fail(ctx, BDF_E_CUDA, why ? why : "launch_deflate", e);
-    if (why) return fail(ctx, BDF_E_UNSUPPORTED, why);
-    return BDF_E_OK;
+    return run_deflate(ctx, a, s, max_len);
 }
 
 int bdf_compress_size_batch_device(bdf_ctx *ctx, int level, const uint8_t *in, const uint64_t *in_off,

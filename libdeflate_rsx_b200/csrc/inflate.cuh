@@ -903,8 +903,10 @@ __device__ __forceinline__ int decode_step(const Grp<G> &g, BitReader &br, OutSt
 }
 
 // read_dynamic_huffman_header, src/decompress/mod.rs:403-507
-template <int G>
-__device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, InflateSmem<G> &sm, uint32_t &nlong)
+// SM: anything with the members of InflateSmem (lit_tab, off_tab, lit_sorted, off_sorted, lit_code,
+// off_code, bs, lens) — the lane kernel passes a view whose tables sit in its own slot layout.
+template <int G, class SM, int LTB = LT_BITS>
+__device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, SM &sm, uint32_t &nlong)
 {
     nlong = 1;
     br.refill();
@@ -979,20 +981,20 @@ __device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, InflateSmem<G
     uint32_t long_off = 0, long_lit = 0;
     if (!build_code<CODE_OFFSET, OT_BITS, G>(g, sm.lens + nlit, noff, sm.off_tab, sm.off_sorted, sm.off_code, sm.bs, &long_off))
         return BDF_BAD_DATA;
-    if (!build_code<CODE_LITLEN, LT_BITS, G>(g, sm.lens, nlit, sm.lit_tab, sm.lit_sorted, sm.lit_code, sm.bs, &long_lit))
+    if (!build_code<CODE_LITLEN, LTB, G>(g, sm.lens, nlit, sm.lit_tab, sm.lit_sorted, sm.lit_code, sm.bs, &long_lit))
         return BDF_BAD_DATA;
     nlong = long_off + long_lit;
     return BDF_OK;
 }
 
-template <int G>
-__device__ void load_static_codes(const Grp<G> &g, InflateSmem<G> &sm)
+template <int G, class SM, int LTB = LT_BITS>
+__device__ void load_static_codes(const Grp<G> &g, SM &sm)
 {
     for (unsigned s = g.lane; s < 320; s += G)
         sm.lens[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : s < 288 ? 8 : 5;
     g.sync();
     build_code<CODE_OFFSET, OT_BITS, G>(g, sm.lens + 288, 32, sm.off_tab, sm.off_sorted, sm.off_code, sm.bs);
-    build_code<CODE_LITLEN, LT_BITS, G>(g, sm.lens, 288, sm.lit_tab, sm.lit_sorted, sm.lit_code, sm.bs);
+    build_code<CODE_LITLEN, LTB, G>(g, sm.lens, 288, sm.lit_tab, sm.lit_sorted, sm.lit_code, sm.bs);
 }
 
 // Raw DEFLATE stream [p, p+len) -> o; returns status, *used = bytes consumed.
@@ -1144,9 +1146,55 @@ struct InflateArgs {
     uint64_t *out_size;
     uint32_t *checksum;
     int32_t *status;
-    unsigned long long *work_counter;
+    unsigned long long *work_counter;    // queue head of inflate_kernel (lane groups)
+    unsigned long long *work_counter2;   // queue head of inflate_lane_kernel
     uint32_t n;
+    // Two engines share a batch: a stream whose capacity is at least split_ratio times its
+    // compressed length ("heavy": a few long matches, run-length / periodic data) goes to the
+    // lane-group kernel, every other stream to the lane-per-stream kernel (inflate_lane.cuh).
+    // 0 = no split: the kernel that is launched takes every stream.
+    uint32_t split_ratio;
 };
+
+// capacities are clamped so that pos + length (<= 65536 + 258 after coalescing) cannot wrap
+constexpr uint32_t INFLATE_CAP_MAX = 0xFFFE0000u;
+__device__ __forceinline__ bool inflate_is_heavy(uint32_t ratio, uint64_t len, uint64_t cap)
+{
+    return ratio != 0 && cap >= (uint64_t)ratio * (len ? len : 1);
+}
+
+// Framing in front of the DEFLATE data (decompress_zlib_uninit / decompress_gzip_uninit,
+// src/decompress/mod.rs:1074-1127,1144-1240): offset and length of the DEFLATE data, or the
+// status that ends the stream.
+template <int FORMAT>
+__device__ __forceinline__ int inflate_frame_header(const uint8_t *p, uint32_t len, uint32_t &at, uint32_t &dlen)
+{
+    at = 0; dlen = 0;
+    if (FORMAT == BDF_RAW) { dlen = len; return BDF_OK; }
+    if (FORMAT == BDF_ZLIB) {
+        if (len < 6) return BDF_SHORT_INPUT;
+        const unsigned hdr = (unsigned)p[0] << 8 | p[1];
+        at = 2;
+        dlen = len - 6;
+        if (hdr % 31 != 0 || ((hdr >> 8) & 0xF) != 8 || ((hdr >> 12) & 0xF) > 7 || ((hdr >> 5) & 1)) return BDF_BAD_DATA;
+        return BDF_OK;
+    }
+    if (len < 18) return BDF_SHORT_INPUT;
+    if (p[0] != 0x1F || p[1] != 0x8B || p[2] != 8 || (p[3] & 0xE0)) return BDF_BAD_DATA;
+    const unsigned flg = p[3];
+    uint64_t h = 10;
+    if (flg & 0x04) {
+        if (h + 2 > len) return BDF_SHORT_INPUT;
+        h += 2 + (p[h] | (uint64_t)p[h + 1] << 8);
+    }
+    if (flg & 0x08) { while (h < len && p[h]) h++; h++; }
+    if (flg & 0x10) { while (h < len && p[h]) h++; h++; }
+    if (flg & 0x02) h += 2;
+    if (h + 8 > len) return BDF_SHORT_INPUT;
+    at = (uint32_t)h;
+    dlen = (uint32_t)(len - 8 - h);
+    return BDF_OK;
+}
 
 constexpr int INF_THREADS = 64;     // threads per CTA; 64 / G lane groups = streams in flight per CTA
 
@@ -1172,25 +1220,39 @@ inflate_kernel(InflateArgs a)
     // groups that start together stay in lock-step (one instruction stream for 32/G streams);
     // groups that fetched on their own would drift apart for good and execute one after the other.
     constexpr unsigned GPW = 32 / G;
+    bool q_empty = false;
     for (;;) {
+        // Every group of the warp takes the next stream of this kernel's class (see
+        // InflateArgs::split_ratio); without a split that is GPW consecutive streams in one round.
+        bool have = false;
         unsigned long long idx = 0;
-        if (lane_id() == 0) idx = atomicAdd(a.work_counter, (unsigned long long)GPW);
-        idx = __shfl_sync(BDF_FULL_MASK, idx, 0);
-        if (idx >= a.n) break;
-        idx += lane_id() / G;
-        const bool have = idx < a.n;
-        const uint8_t *p = a.in;
         uint64_t len64 = 0, cap64 = 0;
+        while (!q_empty) {
+            const unsigned need = __ballot_sync(BDF_FULL_MASK, !have && g.lane == 0);
+            if (!need) break;
+            unsigned long long base = 0;
+            if (lane_id() == 0) base = atomicAdd(a.work_counter, (unsigned long long)__popc(need));
+            base = __shfl_sync(BDF_FULL_MASK, base, 0);
+            if (base + __popc(need) >= a.n) q_empty = true;
+            if (!have) {
+                const unsigned long long my = base + __popc(need & ((1u << g.shift) - 1u));
+                if (my < a.n) {
+                    len64 = a.in_off[my + 1] - a.in_off[my];
+                    cap64 = a.max_out[my];
+                    if (a.split_ratio == 0 || inflate_is_heavy(a.split_ratio, len64, cap64)) { have = true; idx = my; }
+                }
+            }
+        }
+        if (!__any_sync(BDF_FULL_MASK, have)) break;
+        const uint8_t *p = a.in;
         OutState o;
         o.out = a.out;
         if (have) {
             p = a.in + a.in_off[idx];
-            len64 = a.in_off[idx + 1] - a.in_off[idx];
-            cap64 = a.max_out[idx];
             o.out = a.out + a.out_off[idx];
         }
         o.pos = 0;
-        o.cap = cap64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)cap64;
+        o.cap = cap64 > INFLATE_CAP_MAX ? INFLATE_CAP_MAX : (uint32_t)cap64;
         o.npend = 0; o.mylit = 0; o.sumA = 0; o.sumB = 0; o.next_fold = ADLER_FOLD_INTERVAL;
         o.blkcap = BLOCK_BUF_SCRATCH<G>;
         {
@@ -1205,40 +1267,9 @@ inflate_kernel(InflateArgs a)
         int st = BDF_OK;
         uint32_t sum = 0, used = 0, at = 0, dlen = 0;
         const uint32_t len = (uint32_t)len64;
-        if (!have) {
-            st = BDF_BAD_DATA;
-        } else if (len64 > 0xFFFFFFF0ull) {
-            st = BDF_BAD_DATA;      // single streams above 4 GiB are outside this engine's range
-        } else if (FORMAT == BDF_RAW) {
-            dlen = len;
-        } else if (FORMAT == BDF_ZLIB) {
-            // decompress_zlib_uninit, src/decompress/mod.rs:1074-1127
-            if (len < 6) st = BDF_SHORT_INPUT;
-            else {
-                const unsigned hdr = (unsigned)p[0] << 8 | p[1];
-                if (hdr % 31 != 0 || ((hdr >> 8) & 0xF) != 8 || ((hdr >> 12) & 0xF) > 7 || ((hdr >> 5) & 1))
-                    st = BDF_BAD_DATA;
-                at = 2;
-                dlen = len - 6;
-            }
-        } else {
-            // decompress_gzip_uninit, src/decompress/mod.rs:1144-1240
-            if (len < 18) st = BDF_SHORT_INPUT;
-            else if (p[0] != 0x1F || p[1] != 0x8B || p[2] != 8 || (p[3] & 0xE0)) st = BDF_BAD_DATA;
-            else {
-                const unsigned flg = p[3];
-                uint64_t h = 10;
-                if (flg & 0x04) {
-                    if (h + 2 > len) st = BDF_SHORT_INPUT;
-                    else h += 2 + (p[h] | (uint64_t)p[h + 1] << 8);
-                }
-                if (st == BDF_OK && (flg & 0x08)) { while (h < len && p[h]) h++; h++; }
-                if (st == BDF_OK && (flg & 0x10)) { while (h < len && p[h]) h++; h++; }
-                if (st == BDF_OK && (flg & 0x02)) h += 2;
-                if (st == BDF_OK && h + 8 > len) st = BDF_SHORT_INPUT;
-                if (st == BDF_OK) { at = (uint32_t)h; dlen = (uint32_t)(len - 8 - h); }
-            }
-        }
+        if (!have) st = BDF_BAD_DATA;
+        else if (len64 > 0xFFFFFFF0ull) st = BDF_BAD_DATA;      // single streams above 4 GiB are outside this engine's range
+        else st = inflate_frame_header<FORMAT>(p, len, at, dlen);
         const bool go = st == BDF_OK;
         // all lanes of the warp call this together (see inflate_stream)
         const int ist = inflate_stream<FORMAT == BDF_ZLIB, G>(g, p + at, dlen, o, sm, &used, go);
