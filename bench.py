@@ -1,10 +1,10 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the batch DEFLATE engine.
 
-Metric (BASELINE.json): batch decompress GB/s of UNCOMPRESSED bytes.
-Workload at every N: BASELINE.json configs[1] per GPU — 65536 x 64 KiB zlib
-streams of the gen_bench corpus (reference scripts/gen_bench_files.py) — i.e.
-weak scaling: the batch shards by stream, no collective on the data path.
+Metric (BASELINE.json): batch decompress / compress GB/s of UNCOMPRESSED bytes.
+Headline workload at every N: BASELINE.json configs[1] per GPU — 65536 x 64 KiB zlib streams of
+the gen_bench corpus (reference scripts/gen_bench_files.py) — i.e. weak scaling: the batch shards
+by stream, no collective on the data path.
 
 One JSON line on stdout (rank 0).  Keys follow the driver contract:
   value     : device-resident throughput (inputs already in HBM), CUDA events, max over ranks
@@ -12,7 +12,13 @@ One JSON line on stdout (rank 0).  Keys follow the driver contract:
   roofline  : the inflate kernel against the measured HBM copy bandwidth
   cpu_baseline : the C oracle (restatement of the reference's Rust CPU path; the Rust
                  toolchain is absent) on the box's host cores, bounded sample
-`--impl reference` times that CPU restatement as the reference arm.
+and one object per remaining BASELINE config, each with the same four parts (value / kernel_ms,
+roofline, cpu_baseline, e2e):
+  compress_l1, compress_l6 : configs[2], configs[3] — 65536 x 64 KiB of corpus A, byte-identical
+  compress_l12             : configs[3] — level 12 on a stated smaller batch, ratio vs the oracle
+  mixed_pipeline           : configs[4] — corpus B shard: compress -> decompress -> CRC-32
+`--impl reference` times the CPU restatement as the reference arm on the same 65536-stream batch
+(and prints configs[0], 1024 gzip streams, beside it).
 """
 import argparse
 import ctypes as C
@@ -33,6 +39,8 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 STREAM = 65536
 N_STREAMS = 65536
 METRIC = "batch decompress GB/s (uncompressed)"
+ORACLE_NOTE = ("oracle/ C restatement of the reference's Rust CPU batch path (cargo/rustc absent, "
+               "oracle/_ref cannot be built), one codec state per thread")
 
 
 def make_workload(n_streams, fmt_wbits=15, level=6):
@@ -120,51 +128,204 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """DRAM bytes per launch of the inflate kernel from the committed ncu summary, if any."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "inflate_traffic.json")) as f:
-            return json.load(f)
-    except Exception:
-        return None
+def ncu_traffic(key):
+    """DRAM bytes per stream of one kernel from the committed ncu summary (profiles/traffic.json:
+    {key: {dram_bytes_per_stream, streams_in_capture, report}}), if any."""
+    for name in ("traffic.json", "inflate_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                d = json.load(f)
+            if key in d:
+                return d[key]
+            if name == "inflate_traffic.json" and key == "inflate_config2":
+                return d
+        except Exception:
+            pass
+    return None
 
 
-def cpu_baseline(n_sample, min_seconds, plain, flat, in_off):
-    """The oracle's batch inflate on all host cores over the first n_sample streams."""
-    import oracle_lib as o
-    n = n_sample
+def roofline(kernel, alg_bytes, kernel_ms, n_streams, traffic_key):
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    tr = ncu_traffic(traffic_key)
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "frac_of_nominal_8000": achieved / 8000.0,
+            "traffic": (tr["dram_bytes_per_stream"] * n_streams if tr else None),
+            "kernel": kernel, "peak_source": peak_src,
+            "traffic_source": (f"ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch over "
+                               f"{tr['streams_in_capture']} streams ({tr['report']}), scaled per stream to this launch"
+                               if tr else None),
+            "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms}
+
+
+def timed_passes(fn, min_seconds, min_reps=2, max_reps=50):
+    """best wall time of fn() over at least min_reps passes / min_seconds."""
+    best, reps, t_all = None, 0, time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        reps += 1
+        if reps >= max_reps or (reps >= min_reps and time.perf_counter() - t_all >= min_seconds):
+            return best, reps
+
+
+def cpu_decompress(o, flat, in_off, n, fmt, min_seconds):
+    """oracle batch inflate of the first n streams on all host cores -> (GB/s, cores, reps)."""
     sub_off = in_off[:n + 1].copy()
     sub = flat[:int(sub_off[-1])]
     max_out = np.full(n, STREAM, dtype=np.uint64)
     cores = o.num_cores()
     buf = np.zeros(n * STREAM + 1, dtype=np.uint8)      # pre-faulted output, outside the timing
-    best, reps, t_all = None, 0, time.perf_counter()
-    while True:
-        t0 = time.perf_counter()
-        out, out_off, out_size, status = o.decompress_batch(sub, sub_off, max_out, o.ZLIB, cores, out=buf)
-        dt = time.perf_counter() - t0
-        assert (status == 0).all()
-        best = dt if best is None else min(best, dt)
-        reps += 1
-        if reps >= 3 and time.perf_counter() - t_all >= min_seconds:
-            break
-    assert out[:STREAM].tobytes() == plain[0]
-    return {"value": n * STREAM / best / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
-            "sample": f"{n} of the {N_STREAMS} streams ({n * STREAM >> 20} MiB uncompressed), best of {reps} "
-                      f"passes, oracle/ C restatement of the reference CPU batch path "
-                      f"(Rust toolchain unavailable), one codec state per thread"}
+    res = {}
+
+    def one():
+        res["r"] = o.decompress_batch(sub, sub_off, max_out, fmt, cores, out=buf)
+    best, reps = timed_passes(one, min_seconds, min_reps=3)
+    out, out_off, out_size, status = res["r"]
+    assert (status == 0).all()
+    return n * STREAM / best / 1e9, cores, reps, out
 
 
-def pipeline_section(ctx, lib, bdf, dev, stream, n, level, world, barrier, steps=2):
-    """BASELINE configs[4] per-GPU shard: corpus B (mixed text / binary / periodic / low-entropy
-    64 KiB streams) through compress (gzip framing) -> pack -> decompress -> CRC-32 check, all
-    resident in HBM.  16 GiB over 8 GPUs = 2 GiB = 32768 streams per GPU.  Returns per-rank times."""
+def cpu_compress(o, flat, in_off, n, level, fmt, min_seconds):
+    """oracle batch deflate of the first n streams on all host cores -> (GB/s, cores, reps, sizes)."""
+    sub_off = in_off[:n + 1].copy()
+    sub = flat[:int(sub_off[-1])]
+    cores = o.num_cores()
+    bound = int(o.compress_bound(fmt, STREAM))
+    out = np.zeros(n * bound + 1, dtype=np.uint8)
+    out_off = np.arange(n, dtype=np.uint64) * np.uint64(bound)
+    out_size = np.zeros(n, dtype=np.uint64)
+    status = np.zeros(n, dtype=np.int32)
+    L = o.lib()
+
+    def one():
+        L.orc_compress_batch(level, fmt, sub.ctypes.data, sub_off.ctypes.data, n, out.ctypes.data,
+                             out_off.ctypes.data, out_size.ctypes.data, status.ctypes.data, cores)
+    best, reps = timed_passes(one, min_seconds)
+    assert (status == 0).all()
+    return int(sub_off[-1]) / best / 1e9, cores, reps, (out, out_off, out_size)
+
+
+def compress_section(env, level, n, steps, e2e_steps, cpu_sample, cpu_seconds, with_cpu):
+    """BASELINE configs[2] / [3]: n x 64 KiB of corpus A at `level`, raw DEFLATE, device-resident
+    (CUDA events) and through the host call; checked against the oracle inside the bench."""
     import torch
     import corpus
+    ctx, lib, bdf, dev, stream, world = env["ctx"], env["lib"], env["bdf"], env["dev"], env["stream"], env["world"]
+    dist = env["dist"]
+    plain = [corpus.corpus_a_stream(k) for k in range(16)]
+    tile = torch.from_numpy(np.frombuffer(b"".join(plain), dtype=np.uint8).copy()).to(dev)
+    d_plain = tile.repeat(n // 16)
+    d_in_off = torch.arange(n + 1, dtype=torch.int64, device=dev) * STREAM
+    bound = int(lib.bdf_compress_bound(bdf.RAW, STREAM))
+    d_slab = torch.empty(n * bound, dtype=torch.uint8, device=dev)
+    d_slab_off = torch.arange(n, dtype=torch.int64, device=dev) * bound
+    d_size = torch.zeros(n, dtype=torch.int64, device=dev)
+    d_stat = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    sp = C.c_void_p(stream.cuda_stream)
+
+    def step():
+        ctx.check(lib.bdf_compress_batch_device(ctx.handle, level, bdf.RAW, d_plain.data_ptr(), d_in_off.data_ptr(), n,
+                                                d_slab.data_ptr(), d_slab_off.data_ptr(), d_size.data_ptr(),
+                                                d_stat.data_ptr(), sp))
+    launches0 = ctx.kernel_launches
+    step()
+    torch.cuda.synchronize(dev)
+    launches_per_step = ctx.kernel_launches - launches0
+    assert int((d_stat != 0).sum()) == 0
+    sizes = d_size.cpu().numpy()
+    comp_bytes = int(sizes.sum())
+    # parity gate: the 16 distinct streams against the oracle (levels 1..9 byte-identical; 10..12
+    # total size within 0.5 % and every stream inflates to its input under zlib)
+    import oracle_lib as o
+    o.build()
+    got = [d_slab[k * bound:k * bound + int(sizes[k])].cpu().numpy().tobytes() for k in range(16)]
+    exp = [o.compress(p, level) for p in plain]
+    if level <= 9:
+        assert got == exp, f"level {level}: output differs from the oracle"
+    else:
+        assert all(zlib.decompress(g, -15) == p for g, p in zip(got, plain))
+        assert sum(map(len, got)) <= 1.005 * sum(map(len, exp)), "level %d: ratio tolerance" % level
+    assert (sizes.reshape(-1, 16) == sizes[:16]).all()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    env["barrier"]()
+    ev[0].record(stream)
+    for k in range(steps):
+        step()
+        ev[k + 1].record(stream)
+    env["barrier"]()
+    ms = ev[0].elapsed_time(ev[-1]) / steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ubytes = n * STREAM
+    del d_slab
+    torch.cuda.empty_cache()
+
+    # end to end: pinned host input -> bdf_compress_batch_host_dense -> pinned dense output + offsets
+    h_in_p, h_in_bytes = env["pinned_big"]
+    assert h_in_bytes >= ubytes
+    h_in = np.ctypeslib.as_array(C.cast(h_in_p, C.POINTER(C.c_uint8)), shape=(ubytes,))
+    h_tile = np.frombuffer(b"".join(plain), dtype=np.uint8)
+    h_in.reshape(-1, 16 * STREAM)[:] = h_tile
+    h_out_p, h_out_cap = env["pinned_small"]
+    h_in_off = np.arange(n + 1, dtype=np.uint64) * np.uint64(STREAM)
+    h_dense_off = np.zeros(n + 1, dtype=np.uint64)
+    h_stat = np.full(n, -1, dtype=np.int32)
+    assert comp_bytes <= h_out_cap
+
+    def e2e_step():
+        ctx.check(lib.bdf_compress_batch_host_dense(ctx.handle, level, bdf.RAW, h_in_p, h_in_off.ctypes.data, n,
+                                                    h_out_p, h_out_cap, h_dense_off.ctypes.data, h_stat.ctypes.data))
+    e2e_step()
+    assert (h_stat == 0).all() and int(h_dense_off[-1]) == comp_bytes
+    h_out = np.ctypeslib.as_array(C.cast(h_out_p, C.POINTER(C.c_uint8)), shape=(comp_bytes,))
+    k = n - 3
+    assert h_out[int(h_dense_off[k]):int(h_dense_off[k + 1])].tobytes() == got[k % 16]
+    env["barrier"]()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    kname = "bdf::deflate_l1_kernel" if level == 1 else "bdf::deflate_hc_kernel" if level <= 9 else "bdf::deflate_bt_kernel"
+    sec = {
+        "workload": f"compress {n} x 64 KiB of corpus A (gen_bench) per GPU at level {level}, raw DEFLATE; "
+                    + ("byte-identical to the oracle" if level <= 9 else "total size <= 1.005 x the oracle's, zlib round trip"),
+        "unit": "GB/s (uncompressed)", "value": world * ubytes / (ms * 1e-3) / 1e9, "kernel_ms": ms,
+        "steps": steps, "ratio": ubytes / comp_bytes, "gpu_launches_per_step": int(launches_per_step),
+        "roofline": roofline(kname, ubytes + comp_bytes, ms, n, f"deflate_l{level}_corpusA"),
+        "e2e": {"value": world * ubytes / e2e_s / 1e9, "unit": "GB/s", "steps": e2e_steps,
+                "h2d_bytes_per_step": ubytes + (n + 1) * 8, "d2h_bytes_per_step": comp_bytes + (n + 1) * 8 + n * 4,
+                "api": "bdf_compress_batch_host_dense (pinned host buffers)"},
+    }
+    if with_cpu:
+        ns = min(n, cpu_sample)
+        v, cores, reps, (oo, ooff, osz) = cpu_compress(o, h_in, h_in_off, ns, level, o.RAW, cpu_seconds)
+        assert oo[int(ooff[1]):int(ooff[1]) + int(osz[1])].tobytes() == exp[1]
+        sec["cpu_baseline"] = {"value": v, "unit": "GB/s", "cores": cores, "kind": "port",
+                               "sample": f"{ns} of the {n} streams ({ns * STREAM >> 20} MiB), best of {reps} passes, " + ORACLE_NOTE}
+    return sec
+
+
+def pipeline_section(env, n, level, steps, e2e_steps, cpu_sample, cpu_seconds, with_cpu):
+    """BASELINE configs[4] per-GPU shard: corpus B (mixed text / binary / periodic / low-entropy
+    64 KiB streams) through compress (gzip framing) -> pack -> decompress -> CRC-32 check, all
+    resident in HBM.  16 GiB over 8 GPUs = 2 GiB = 32768 streams per GPU."""
+    import torch
+    import corpus
+    ctx, lib, bdf, dev, stream, world = env["ctx"], env["lib"], env["bdf"], env["dev"], env["stream"], env["world"]
+    dist = env["dist"]
     base = [corpus.corpus_b_stream(k) for k in range(64)]
     crc = np.array([zlib.crc32(b) for b in base], dtype=np.uint32)
     tile = np.frombuffer(b"".join(base), dtype=np.uint8)
-    d_plain = torch.from_numpy(np.tile(tile, n // 64)).to(dev)
+    d_plain = torch.from_numpy(tile.copy()).to(dev).repeat(n // 64)
     d_in_off = torch.arange(n + 1, dtype=torch.int64, device=dev) * STREAM
     bound = int(lib.bdf_compress_bound(bdf.GZIP, STREAM))
     d_slab = torch.empty(n * bound, dtype=torch.uint8, device=dev)
@@ -204,52 +365,142 @@ def pipeline_section(ctx, lib, bdf, dev, stream, n, level, world, barrier, steps
             ev[3].record(stream)
         return ok
 
+    launches0 = ctx.kernel_launches
     assert bool(one(False).item()), "pipeline parity (CRC-32 of the round trip) failed"
+    launches_per_step = ctx.kernel_launches - launches0
     assert d_out[(n - 1) * STREAM:].cpu().numpy().tobytes() == base[(n - 1) % 64]
-    barrier()
+    env["barrier"]()
     t_c = t_p = t_d = 0.0
     for _ in range(steps):
         ok = one(True)
         torch.cuda.synchronize(dev)
         assert bool(ok.item())
         t_c += ev[0].elapsed_time(ev[1]); t_p += ev[1].elapsed_time(ev[2]); t_d += ev[2].elapsed_time(ev[3])
-    barrier()
+    env["barrier"]()
     comp_bytes = int(d_csize.sum().item())
-    return {"t_compress_ms": t_c / steps, "t_pack_ms": t_p / steps, "t_decompress_ms": t_d / steps,
-            "bytes": n * STREAM, "comp_bytes": comp_bytes}
+    tt = torch.tensor([t_c / steps, t_p / steps, t_d / steps, (t_c + t_p + t_d) / steps], dtype=torch.float64, device=dev)
+    cb = torch.tensor([comp_bytes], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cb, op=dist.ReduceOp.SUM)
+    tc, tp, td, tall = [float(x) for x in tt.tolist()]
+    ub = world * n * STREAM
+    del d_slab, d_dense, d_out, d_plain
+    torch.cuda.empty_cache()
+
+    # end to end through the host calls: compress (dense result) -> decompress, CRC-32 checked on the host
+    ubytes = n * STREAM
+    h_big_p, h_big_bytes = env["pinned_big"]
+    assert h_big_bytes >= 2 * ubytes
+    h_in = np.ctypeslib.as_array(C.cast(h_big_p, C.POINTER(C.c_uint8)), shape=(2 * ubytes,))
+    h_in[:ubytes].reshape(-1, 64 * STREAM)[:] = tile
+    h_out_p = h_big_p + ubytes
+    h_mid_p, h_mid_cap = env["pinned_mid"](comp_bytes + 4096)
+    h_in_off = np.arange(n + 1, dtype=np.uint64) * np.uint64(STREAM)
+    h_out_off = h_in_off[:n].copy()
+    h_dense_off = np.zeros(n + 1, dtype=np.uint64)
+    h_cstat = np.full(n, -1, dtype=np.int32)
+    h_max = np.full(n, STREAM, dtype=np.uint64)
+    h_size = np.zeros(n, dtype=np.uint64)
+    h_stat = np.full(n, -1, dtype=np.int32)
+    h_sum = np.zeros(n, dtype=np.uint32)
+    exp_crc = np.tile(crc, n // 64)
+    e2e_t = [0.0, 0.0]
+
+    def e2e_step():
+        t0 = time.perf_counter()
+        ctx.check(lib.bdf_compress_batch_host_dense(ctx.handle, level, bdf.GZIP, h_big_p, h_in_off.ctypes.data, n,
+                                                    h_mid_p, h_mid_cap, h_dense_off.ctypes.data, h_cstat.ctypes.data))
+        t1 = time.perf_counter()
+        ctx.check(lib.bdf_decompress_batch_host(ctx.handle, bdf.GZIP, h_mid_p, h_dense_off.ctypes.data, n, h_out_p,
+                                                h_out_off.ctypes.data, h_max.ctypes.data, h_size.ctypes.data,
+                                                h_sum.ctypes.data, h_stat.ctypes.data))
+        t2 = time.perf_counter()
+        assert (h_cstat == 0).all() and (h_stat == 0).all() and (h_sum == exp_crc).all()
+        e2e_t[0] += t1 - t0
+        e2e_t[1] += t2 - t1
+    e2e_step()
+    assert h_in[ubytes + (n - 1) * STREAM:].tobytes() == base[(n - 1) % 64]
+    e2e_t[:] = [0.0, 0.0]
+    env["barrier"]()
+    for _ in range(e2e_steps):
+        e2e_step()
+    t = torch.tensor([e2e_t[0] / e2e_steps, e2e_t[1] / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ec, ed = [float(x) for x in t.tolist()]
+    cbytes = int(cb.item())
+    pipe = {
+        "workload": f"corpus B (mixed text/binary/periodic/low-entropy), {n * STREAM >> 20} MiB per GPU, "
+                    f"level {level} gzip: compress -> pack -> decompress, CRC-32 of every "
+                    f"stream checked against the input's", "unit": "GB/s (uncompressed)",
+        "value": ub / (tall * 1e-3) / 1e9, "pipeline": ub / (tall * 1e-3) / 1e9, "compress": ub / (tc * 1e-3) / 1e9,
+        "decompress": ub / (td * 1e-3) / 1e9, "compress_ms": tc, "decompress_ms": td, "pack_ms": tp,
+        "ratio": ub / cbytes, "gpu_launches_per_step": int(launches_per_step),
+        "roofline": roofline("bdf::deflate_hc_kernel + bdf::inflate_lane_kernel / inflate_kernel (whole pipeline)",
+                             2 * (n * STREAM + comp_bytes), tall, n, "mixed_pipeline"),
+        "roofline_compress": roofline("bdf::deflate_hc_kernel", n * STREAM + comp_bytes, tc, n, f"deflate_l{level}_corpusB"),
+        "roofline_decompress": roofline("bdf::inflate_lane_kernel + bdf::inflate_kernel", n * STREAM + comp_bytes, td, n, "inflate_corpusB"),
+        "e2e": {"value": ub / (ec + ed) / 1e9, "compress": ub / ec / 1e9, "decompress": ub / ed / 1e9, "unit": "GB/s",
+                "steps": e2e_steps, "h2d_bytes_per_step": ubytes + comp_bytes + (4 * n + 2) * 8,
+                "d2h_bytes_per_step": ubytes + comp_bytes + (n + 1) * 8 + n * 20,
+                "api": "bdf_compress_batch_host_dense -> bdf_decompress_batch_host (pinned host buffers)"},
+    }
+    if with_cpu:
+        import oracle_lib as o
+        o.build()
+        ns = min(n, cpu_sample)
+        vc, cores, reps, (oo, ooff, osz) = cpu_compress(o, h_in, h_in_off, ns, level, o.GZIP, cpu_seconds)
+        cflat = np.concatenate([oo[int(ooff[i]):int(ooff[i]) + int(osz[i])] for i in range(ns)])
+        coff = np.zeros(ns + 1, dtype=np.uint64)
+        coff[1:] = np.cumsum(osz)
+        vd, _, reps_d, outp = cpu_decompress(o, cflat, coff, ns, o.GZIP, min(cpu_seconds, 2.0))
+        assert outp[:STREAM].tobytes() == base[0]
+        pipe["cpu_baseline"] = {"value": 1.0 / (1.0 / vc + 1.0 / vd), "compress": vc, "decompress": vd, "unit": "GB/s",
+                                "cores": cores, "kind": "port",
+                                "sample": f"{ns} of the {n} streams ({ns * STREAM >> 20} MiB): compress best of {reps}, "
+                                          f"decompress best of {reps_d} passes, " + ORACLE_NOTE}
+    return pipe
 
 
 def run_reference(args):
-    """Reference arm: the CPU restatement on the host cores, same metric / config."""
+    """Reference arm: the CPU restatement on the host cores, same metric / config (all 65536
+    streams per step); BASELINE configs[0] (1024 x 64 KiB gzip, level 6) is printed beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle_lib as o
     o.build()
-    n = 4096
+    n = args.streams
     plain, flat, in_off, _ = make_workload(n)
     max_out = np.full(n, STREAM, dtype=np.uint64)
     cores = o.num_cores()
     buf = np.zeros(n * STREAM + 1, dtype=np.uint8)      # pre-faulted output, outside the timing
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 1)):
         o.decompress_batch(flat, in_off, max_out, o.ZLIB, cores, out=buf)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         out, out_off, out_size, status = o.decompress_batch(flat, in_off, max_out, o.ZLIB, cores, out=buf)
     dt = (time.perf_counter() - t0) / args.steps
     assert (status == 0).all() and out[:STREAM].tobytes() == plain[0]
+    assert out[(n - 1) * STREAM:n * STREAM].tobytes() == plain[(n - 1) % 16]
     v = n * STREAM / dt / 1e9
-    sample = (f"each step = {n} of the {N_STREAMS} streams ({n * STREAM >> 20} MiB uncompressed) on "
-              f"{cores} host threads; oracle/ C restatement of the reference's Rust CPU path "
-              f"(cargo/rustc absent, oracle/_ref cannot be built)")
+    # configs[0]: 1024 x 64 KiB gzip buffers (level 6, gen_bench corpus), CPU batch decompress
+    n0 = 1024
+    _, flat0, off0, _ = make_workload(n0, fmt_wbits=31)
+    v0, _, reps0, _ = cpu_decompress(o, flat0, off0, n0, o.GZIP, 2.0)
+    sample = (f"each step = all {n} streams ({n * STREAM >> 20} MiB uncompressed) on {cores} host threads; " + ORACLE_NOTE)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "decompress 65536 x 64 KiB zlib streams (gen_bench corpus, level 6), "
-                               "bounded sample per step", "format": "zlib", "stream_bytes": STREAM},
+        "config": {"workload": f"decompress {n} x 64 KiB zlib streams per GPU (BASELINE configs[1]; gen_bench "
+                               f"corpus, system-zlib level 6), Adler-32 verified in-kernel",
+                   "format": "zlib", "streams_per_gpu": n, "stream_bytes": STREAM},
         "cpu_baseline": {"value": v, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config0": {"workload": "BASELINE configs[0]: CPU batch decompress of 1024 x 64 KiB gzip buffers (level 6, "
+                                "gen_bench corpus)", "value": v0, "unit": "GB/s", "cores": cores, "passes": reps0},
     }), flush=True)
 
 
@@ -265,6 +516,8 @@ def main():
     ap.add_argument("--pipeline-streams", type=int, default=32768,
                     help="streams per GPU of the mixed-corpus compress+decompress+CRC pipeline (0 = skip)")
     ap.add_argument("--pipeline-level", type=int, default=6)
+    ap.add_argument("--compress-levels", default="1,6,12", help="levels of the compress sections ('' = skip)")
+    ap.add_argument("--l12-streams", type=int, default=2048, help="streams per GPU of the level >= 10 section")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -354,8 +607,9 @@ def main():
 
     # ---- end-to-end arm: host C-ABI call, pinned host buffers, H2D + D2H inside the timed region
     e2e_steps = args.e2e_steps or max(3, min(args.steps, 5))
+    big_bytes = max(out_bytes, 2 * (args.pipeline_streams // 64 * 64) * STREAM) + 64
     h_in_p = lib.bdf_host_alloc(comp_bytes + 64)
-    h_out_p = lib.bdf_host_alloc(out_bytes + 64)
+    h_out_p = lib.bdf_host_alloc(big_bytes)
     if not h_in_p or not h_out_p:
         raise SystemExit("pinned host allocation failed")
     h_in = np.ctypeslib.as_array(C.cast(h_in_p, C.POINTER(C.c_uint8)), shape=(comp_bytes,))
@@ -391,37 +645,38 @@ def main():
     h2d = comp_bytes + (n + 1) * 8 + 2 * n * 8
     d2h = out_bytes + n * 8 + n * 4 + n * 4
 
-    # ---- configs[4]: mixed corpus, compress -> decompress -> CRC-32, sharded by stream (extra section)
-    pipe = None
+    # ---- the other BASELINE configs (extra objects of the same line)
+    mids = {}
+
+    def pinned_mid(nbytes):
+        if "p" not in mids or mids["cap"] < nbytes:
+            if "p" in mids:
+                lib.bdf_host_free(mids["p"])
+            mids["p"], mids["cap"] = lib.bdf_host_alloc(nbytes), nbytes
+            if not mids["p"]:
+                raise SystemExit("pinned host allocation failed")
+        return mids["p"], mids["cap"]
+    with_cpu = world == 1 and not args.no_cpu_baseline
+    env = {"ctx": ctx, "lib": lib, "bdf": bdf, "dev": dev, "stream": stream, "world": world, "dist": dist,
+           "barrier": barrier, "pinned_big": (h_out_p, big_bytes), "pinned_small": pinned_mid(192 << 20),
+           "pinned_mid": pinned_mid}
+    extra = {}
+    levels = [int(x) for x in args.compress_levels.split(",") if x.strip()]
+    for level in levels:
+        if level >= 10:
+            nl, st_, es_, cs_ = min(n, args.l12_streams) // 16 * 16, 2, 2, 64
+        elif level >= 2:
+            nl, st_, es_, cs_ = n, 5, 2, 1024
+        else:
+            nl, st_, es_, cs_ = n, 10, 3, 4096
+        if nl >= 16:
+            extra[f"compress_l{level}"] = compress_section(env, level, nl, st_, es_, cs_, 3.0, with_cpu)
     if args.pipeline_streams >= 64:
-        lib.bdf_host_free(h_out_p)
-        h_out_p = None
-        torch.cuda.empty_cache()
-        launches_p0 = ctx.kernel_launches
-        pr = pipeline_section(ctx, lib, bdf, dev, stream, args.pipeline_streams // 64 * 64, args.pipeline_level,
-                              world, barrier)
-        tt = torch.tensor([pr["t_compress_ms"], pr["t_pack_ms"], pr["t_decompress_ms"],
-                           pr["t_compress_ms"] + pr["t_pack_ms"] + pr["t_decompress_ms"]],
-                          dtype=torch.float64, device=dev)
-        cb = torch.tensor([pr["comp_bytes"]], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dist.all_reduce(cb, op=dist.ReduceOp.SUM)
-        tc, tp, td, tall = [float(x) for x in tt.tolist()]
-        ub = world * pr["bytes"]
-        pipe = {"workload": f"corpus B (mixed text/binary/periodic/low-entropy), {pr['bytes'] >> 20} MiB per GPU, "
-                            f"level {args.pipeline_level} gzip: compress -> pack -> decompress, CRC-32 of every "
-                            f"stream checked against the input's", "unit": "GB/s (uncompressed)",
-                "pipeline": ub / (tall * 1e-3) / 1e9, "compress": ub / (tc * 1e-3) / 1e9,
-                "decompress": ub / (td * 1e-3) / 1e9, "pack_ms": tp, "ratio": ub / int(cb.item()),
-                "kernel_launches_per_step": int((ctx.kernel_launches - launches_p0) // 3)}
+        extra["mixed_pipeline"] = pipeline_section(env, args.pipeline_streams // 64 * 64, args.pipeline_level,
+                                                   2, 2, 4096, 3.0, with_cpu)
 
     if rank == 0:
-        peak, peak_src = measured_peak()
         kernel_ms = float(np.mean(step_ms))
-        alg_bytes = comp_bytes + out_bytes
-        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-        traffic = ncu_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -437,25 +692,24 @@ def main():
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "bdf_decompress_batch_host (pinned host buffers)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
-                         "traffic": (traffic["dram_bytes_per_stream"] * n if traffic else None),
-                         "kernel": "bdf::inflate_kernel<BDF_ZLIB>", "peak_source": peak_src,
-                         "traffic_source": (f"ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch over "
-                                            f"{traffic['streams_in_capture']} streams ({traffic['report']}), scaled per stream to this launch" if traffic else None),
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms},
+            "roofline": roofline("bdf::inflate_kernel<BDF_ZLIB>", comp_bytes + out_bytes, kernel_ms, n, "inflate_config2"),
             "clocks": clocks.summary(),
         }
-        if pipe:
-            line["mixed_pipeline"] = pipe
-        if world == 1 and not args.no_cpu_baseline:
+        line.update(extra)
+        if with_cpu:
             import oracle_lib as o
             o.build()
-            line["cpu_baseline"] = cpu_baseline(min(n, 4096), 5.0, plain, flat, in_off)
+            ns = min(n, 4096)
+            v, cores, reps, outp = cpu_decompress(o, flat, in_off, ns, o.ZLIB, 4.0)
+            assert outp[:STREAM].tobytes() == plain[0]
+            line["cpu_baseline"] = {"value": v, "unit": "GB/s", "cores": cores, "kind": "port",
+                                    "sample": f"{ns} of the {n} streams ({ns * STREAM >> 20} MiB uncompressed), best of "
+                                              f"{reps} passes, " + ORACLE_NOTE}
         print(json.dumps(line), flush=True)
     lib.bdf_host_free(h_in_p)
-    if h_out_p:
-        lib.bdf_host_free(h_out_p)
+    lib.bdf_host_free(h_out_p)
+    if "p" in mids:
+        lib.bdf_host_free(mids["p"])
     if world > 1:
         dist.destroy_process_group()
 

@@ -31,9 +31,12 @@ for m in want:
         os.environ.pop(k, None)
     os.environ.update(ENV[m])
     ctxs[m] = b.Context(0)
+only = os.environ.get("KINDS")
 for kind, gen in KINDS.items():
+    if only and kind not in only.split(","):
+        continue
     plain = [gen(k) for k in range(64)]
-    for level, who in ((6, "oracle"), (6, "zlib")):
+    for level, who in ((6, "oracle"), (6, "zlib"))[:int(os.environ.get("PRODUCERS", "2"))]:
         if who == "oracle":
             comp = [o.compress(p, level, b.ZLIB) for p in plain]
         else:

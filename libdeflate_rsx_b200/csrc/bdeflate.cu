@@ -60,9 +60,10 @@ struct bdf_ctx {
     int inflate_group = 16;                     // lanes per stream in inflate_kernel (BDF_INFLATE_GROUP)
     int inflate_mode = 0;                       // 0 = both engines, split by expansion ratio; 1 = lane groups only; 2 = lane per stream only (BDF_INFLATE_MODE)
     int inflate_split = 16;                     // expansion ratio from which a stream goes to the lane-group kernel (BDF_INFLATE_SPLIT)
-    int lane_cfg = 0;                           // 0: 9-bit table, 1 KiB ring (2 warps / SM); 1: 8-bit table, 512 B ring (3 warps / SM) (BDF_LANE_CFG)
+    int lane_cfg = 0;                           // direct-table bits of inflate_lane_kernel: 0 = (8, 7), 7 warps / SM; 1 = (9, 6), 5 warps / SM (BDF_LANE_CFG)
+    int lane_warps_per_sm = 0;                  // cap on resident warps of inflate_lane_kernel, 0 = what fits (BDF_LANE_WARPS)
     bdf::DeflateScratch deflate_scratch;
-    DevBuf in, out, in_off, out_off, max_out, out_size, status, checksum;
+    DevBuf in, out, in_off, out_off, max_out, out_size, status, checksum, lane_scratch;
     DevBuf u_in_off, u_tmp_off, u_size, u_status, u_flags, u_begin, u_tmp;     // chunked compression (units)
 };
 
@@ -145,21 +146,25 @@ int launch_inflate_g(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
     return 0;
 }
 
-template <int FORMAT, int LTB, int RING>
-int launch_inflate_lane_c(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
+template <int FORMAT, int LTB, int OTB>
+int launch_inflate_lane_c(bdf_ctx *ctx, bdf::InflateArgs a, cudaStream_t s)
 {
-    const size_t smem = sizeof(bdf::LaneSmem<LTB, RING>);
+    const size_t smem = sizeof(bdf::LaneSmem<LTB, OTB>);
     int &bps = ctx->lane_blocks_per_sm[FORMAT];
     if (bps == 0) {
-        CK(cudaFuncSetAttribute(bdf::inflate_lane_kernel<FORMAT, LTB, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(bdf::inflate_lane_kernel<FORMAT, LTB, RING>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, bdf::inflate_lane_kernel<FORMAT, LTB, RING>, 32, smem));
+        CK(cudaFuncSetAttribute(bdf::inflate_lane_kernel<FORMAT, LTB, OTB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(bdf::inflate_lane_kernel<FORMAT, LTB, OTB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, bdf::inflate_lane_kernel<FORMAT, LTB, OTB>, 32, smem));
         if (bps < 1) bps = 1;
+        if (ctx->lane_warps_per_sm > 0 && ctx->lane_warps_per_sm < bps) bps = ctx->lane_warps_per_sm;
     }
     unsigned long long want = ((unsigned long long)a.n + 31) / 32;
     unsigned long long full = (unsigned long long)ctx->sm_count * bps;
     unsigned grid = (unsigned)(want < full ? want : full);
-    bdf::inflate_lane_kernel<FORMAT, LTB, RING><<<grid, 32, smem, s>>>(a);
+    int rc = ensure(ctx, ctx->lane_scratch, (size_t)full * 32 * bdf::LANE_SORTED_BYTES);
+    if (rc) return rc;
+    a.lane_scratch = (uint8_t *)ctx->lane_scratch.p;
+    bdf::inflate_lane_kernel<FORMAT, LTB, OTB><<<grid, 32, smem, s>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -168,8 +173,8 @@ int launch_inflate_lane_c(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t 
 template <int FORMAT>
 int launch_inflate_lane(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
 {
-    if (ctx->lane_cfg == 1) return launch_inflate_lane_c<FORMAT, 8, 512>(ctx, a, s);
-    return launch_inflate_lane_c<FORMAT, 9, 1024>(ctx, a, s);
+    if (ctx->lane_cfg == 1) return launch_inflate_lane_c<FORMAT, 9, 6>(ctx, a, s);
+    return launch_inflate_lane_c<FORMAT, 8, 7>(ctx, a, s);
 }
 
 template <int FORMAT>
@@ -249,6 +254,7 @@ int bdf_ctx_create(int device, bdf_ctx **out)
         if (v >= 1 && v <= 1032) ctx->inflate_split = v;
     }
     if (const char *e = getenv("BDF_LANE_CFG")) ctx->lane_cfg = atoi(e) == 1 ? 1 : 0;
+    if (const char *e = getenv("BDF_LANE_WARPS")) ctx->lane_warps_per_sm = atoi(e) > 0 ? atoi(e) : 0;
     {
         // Device-to-host result copies per call.  Eight concurrent copies are best when one process
         // owns the host (56.6 vs 51 GB/s); with several ranks returning results to the same host at once
@@ -293,7 +299,7 @@ void bdf_ctx_destroy(bdf_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->in, &ctx->out, &ctx->in_off, &ctx->out_off, &ctx->max_out,
-                      &ctx->out_size, &ctx->status, &ctx->checksum, &ctx->u_in_off, &ctx->u_tmp_off,
+                      &ctx->out_size, &ctx->status, &ctx->checksum, &ctx->lane_scratch, &ctx->u_in_off, &ctx->u_tmp_off,
                       &ctx->u_size, &ctx->u_status, &ctx->u_flags, &ctx->u_begin, &ctx->u_tmp};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -420,6 +426,7 @@ static int decompress_device_locked(bdf_ctx *ctx, int format, const uint8_t *in,
     a.in = in; a.in_off = in_off; a.out = out; a.out_off = out_off; a.max_out = max_out;
     a.out_size = out_size; a.checksum = checksum; a.status = status; a.n = (uint32_t)n;
     a.split_ratio = 0;
+    a.lane_scratch = nullptr;
     a.work_counter = next_counter(ctx, s);
     a.work_counter2 = next_counter(ctx, s);
     if (!a.work_counter || !a.work_counter2) return fail(ctx, BDF_E_CUDA, "cudaMemsetAsync(work counter)");

@@ -905,7 +905,11 @@ __device__ __forceinline__ int decode_step(const Grp<G> &g, BitReader &br, OutSt
 // read_dynamic_huffman_header, src/decompress/mod.rs:403-507
 // SM: anything with the members of InflateSmem (lit_tab, off_tab, lit_sorted, off_sorted, lit_code,
 // off_code, bs, lens) — the lane kernel passes a view whose tables sit in its own slot layout.
-template <int G, class SM, int LTB = LT_BITS>
+// where the precode table lives while a header is read (128 entries): on top of the offset table
+// unless the holder says otherwise
+template <class SM> __device__ __forceinline__ uint16_t *precode_table(SM &sm) { return sm.off_tab; }
+
+template <int G, class SM, int LTB = LT_BITS, int OTB = OT_BITS>
 __device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, SM &sm, uint32_t &nlong)
 {
     nlong = 1;
@@ -935,7 +939,7 @@ __device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, SM &sm, uint3
         g.sync();
     }
     if (br.overrun()) return BDF_SHORT_INPUT;
-    uint16_t *pre_tab = sm.off_tab;
+    uint16_t *pre_tab = precode_table(sm);
     if (!build_code<CODE_PRECODE, PT_BITS, G>(g, pre_lens, 19, pre_tab, sm.off_sorted, sm.off_code, sm.bs))
         return BDF_BAD_DATA;
     // run-length decode of the litlen + offset code lengths (group-uniform)
@@ -979,7 +983,7 @@ __device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, SM &sm, uint3
     if (br.overrun()) return BDF_SHORT_INPUT;
     g.sync();
     uint32_t long_off = 0, long_lit = 0;
-    if (!build_code<CODE_OFFSET, OT_BITS, G>(g, sm.lens + nlit, noff, sm.off_tab, sm.off_sorted, sm.off_code, sm.bs, &long_off))
+    if (!build_code<CODE_OFFSET, OTB, G>(g, sm.lens + nlit, noff, sm.off_tab, sm.off_sorted, sm.off_code, sm.bs, &long_off))
         return BDF_BAD_DATA;
     if (!build_code<CODE_LITLEN, LTB, G>(g, sm.lens, nlit, sm.lit_tab, sm.lit_sorted, sm.lit_code, sm.bs, &long_lit))
         return BDF_BAD_DATA;
@@ -987,13 +991,13 @@ __device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, SM &sm, uint3
     return BDF_OK;
 }
 
-template <int G, class SM, int LTB = LT_BITS>
+template <int G, class SM, int LTB = LT_BITS, int OTB = OT_BITS>
 __device__ void load_static_codes(const Grp<G> &g, SM &sm)
 {
     for (unsigned s = g.lane; s < 320; s += G)
         sm.lens[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : s < 288 ? 8 : 5;
     g.sync();
-    build_code<CODE_OFFSET, OT_BITS, G>(g, sm.lens + 288, 32, sm.off_tab, sm.off_sorted, sm.off_code, sm.bs);
+    build_code<CODE_OFFSET, OTB, G>(g, sm.lens + 288, 32, sm.off_tab, sm.off_sorted, sm.off_code, sm.bs);
     build_code<CODE_LITLEN, LTB, G>(g, sm.lens, 288, sm.lit_tab, sm.lit_sorted, sm.lit_code, sm.bs);
 }
 
@@ -1148,6 +1152,7 @@ struct InflateArgs {
     int32_t *status;
     unsigned long long *work_counter;    // queue head of inflate_kernel (lane groups)
     unsigned long long *work_counter2;   // queue head of inflate_lane_kernel
+    uint8_t *lane_scratch;               // inflate_lane_kernel: LANE_SORTED_BYTES per lane of the grid
     uint32_t n;
     // Two engines share a batch: a stream whose capacity is at least split_ratio times its
     // compressed length ("heavy": a few long matches, run-length / periodic data) goes to the
