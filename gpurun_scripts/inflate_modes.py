@@ -16,7 +16,7 @@ import libdeflate_rsx_b200 as b
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 want = sys.argv[2:] or ["group", "lane0", "lane1", "auto"]
 ENV = {"group": {"BDF_INFLATE_MODE": "group"}, "lane0": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "0"},
-       "lane1": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "1"}, "auto": {"BDF_INFLATE_MODE": "auto"}}
+       "lane1": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "1"}, "lane2": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "2"}, "auto": {"BDF_INFLATE_MODE": "auto"}}
 dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(dev)
 torch.cuda.set_stream(stream)

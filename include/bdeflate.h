@@ -139,6 +139,24 @@ int bdf_compress_batch_host(bdf_ctx *ctx, int level, int format, const uint8_t *
                             int32_t *status);
 
 /*
+ * The same call with the result packed: stream i is out[out_off[i] .. out_off[i+1]) (out_off has
+ * n + 1 entries, written by the call; a failed stream is empty, like the reference's empty Vec,
+ * src/batch.rs:52-53).  This is what a `Vec<Vec<u8>>` result is sliced from (src/batch.rs:34-57,
+ * src/batch_cuda.rs:116-141) without a bound-sized host slab: out only needs room for what the batch
+ * compresses to (out_cap bytes; BDF_E_ARG if it is too small, the needed size is then in out_off[n]).
+ * The result is packed on the device and comes back in one copy.
+ * bdf_compress_batch_host_sg takes the input the way `&[&[u8]]` holds it — n pointers and n lengths —
+ * so the caller does not have to flatten it: the library packs the buffers into pinned staging
+ * memory chunk by chunk while earlier chunks are already on their way to the device.
+ */
+int bdf_compress_batch_host_dense(bdf_ctx *ctx, int level, int format, const uint8_t *in,
+                                  const uint64_t *in_off, size_t n, uint8_t *out, size_t out_cap,
+                                  uint64_t *out_off, int32_t *status);
+int bdf_compress_batch_host_sg(bdf_ctx *ctx, int level, int format, const uint8_t *const *in_ptrs,
+                               const size_t *in_lens, size_t n, uint8_t *out, size_t out_cap,
+                               uint64_t *out_off, int32_t *status);
+
+/*
  * Compressor::compress(chunk, out, FlushMode) for many chunks at once (src/compress/mod.rs:693-790)
  * — the call DeflateEncoder::flush_buffer makes for every 256 KiB chunk of its buffer
  * (src/stream.rs:42-196).  Unit i = in[unit_off[i] .. unit_off[i+1]) (at most 262144 bytes),

@@ -22,6 +22,7 @@ EXPORTS = [
     "bdf_compress_batch_device", "bdf_compress_batch_host", "bdf_checksum_batch_device",
     "bdf_checksum_batch_host", "bdf_gather_streams_device", "bdf_compress_units_host",
     "bdf_compress_size_batch_device", "bdf_compress_size_batch_host",
+    "bdf_compress_batch_host_dense", "bdf_compress_batch_host_sg",
 ]
 
 
@@ -62,6 +63,10 @@ def load():
     L.bdf_compress_batch_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, sz, vp, vp, vp, vp, vp]
     L.bdf_compress_batch_host.restype = C.c_int
     L.bdf_compress_batch_host.argtypes = [vp, C.c_int, C.c_int, vp, vp, sz, vp, vp, vp, vp]
+    L.bdf_compress_batch_host_dense.restype = C.c_int
+    L.bdf_compress_batch_host_dense.argtypes = [vp, C.c_int, C.c_int, vp, vp, sz, vp, sz, vp, vp]
+    L.bdf_compress_batch_host_sg.restype = C.c_int
+    L.bdf_compress_batch_host_sg.argtypes = [vp, C.c_int, C.c_int, vp, vp, sz, vp, sz, vp, vp]
     L.bdf_checksum_batch_device.restype = C.c_int
     L.bdf_checksum_batch_device.argtypes = [vp, C.c_int, vp, vp, sz, vp, vp]
     L.bdf_checksum_batch_host.restype = C.c_int

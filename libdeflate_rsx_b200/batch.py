@@ -117,7 +117,41 @@ class BatchCompressor:
             _ptr(out_off), _ptr(out_size), _ptr(status)))
         return out, out_off, out_size, status
 
+    def compress_dense(self, flat, in_off):
+        """Flat input, packed result: returns (out, out_off[n+1], status); stream i is
+        out[out_off[i]:out_off[i+1]] (empty when it failed)."""
+        n = len(in_off) - 1
+        cap = int(in_off[-1]) + (int(in_off[-1]) // 65535 + n) * 5 + n * 28 + 64      # >= the sum of the bounds
+        out = np.empty(cap, dtype=np.uint8)
+        out_off = np.zeros(n + 1, dtype=np.uint64)
+        status = np.zeros(n, dtype=np.int32)
+        self.ctx.check(self.ctx._lib.bdf_compress_batch_host_dense(
+            self.ctx.handle, self.level, self.format, _ptr(flat), _ptr(in_off), n, _ptr(out), cap,
+            _ptr(out_off), _ptr(status)))
+        return out, out_off, status
+
     def compress_batch(self, inputs):
+        """compress_batch(&[&[u8]]) -> Vec<Vec<u8>> (src/batch.rs:20-58): the buffers are handed over
+        as they are (pointer + length each, no flattening on this side) and the packed result is
+        sliced into one bytes object per stream."""
+        n = len(inputs)
+        if n == 0:
+            return []
+        keep = [b if isinstance(b, bytes) else bytes(b) for b in inputs]
+        lens = (C.c_size_t * n)(*[len(b) for b in keep])
+        ptrs = (C.c_char_p * n)(*keep)
+        total = sum(len(b) for b in keep)
+        cap = total + (total // 65535 + n) * 5 + n * 28 + 64
+        out = np.empty(cap, dtype=np.uint8)
+        out_off = np.zeros(n + 1, dtype=np.uint64)
+        status = np.zeros(n, dtype=np.int32)
+        self.ctx.check(self.ctx._lib.bdf_compress_batch_host_sg(
+            self.ctx.handle, self.level, self.format, C.cast(ptrs, C.c_void_p), C.cast(lens, C.c_void_p), n,
+            _ptr(out), cap, _ptr(out_off), _ptr(status)))
+        return [out[int(out_off[i]):int(out_off[i + 1])].tobytes() if status[i] == N.OK else b"" for i in range(n)]
+
+    def compress_batch_slots(self, inputs):
+        """The same through the bound-spaced slab call (bdf_compress_batch_host)."""
         if len(inputs) == 0:
             return []
         flat, in_off = flatten(inputs)

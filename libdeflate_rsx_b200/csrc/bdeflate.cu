@@ -26,6 +26,7 @@ namespace {
 // staging slabs are sized from caller-supplied offsets: refuse anything above 2^46 bytes outright
 // (far above any GPU's memory) so that sums cannot wrap
 constexpr uint64_t BDF_MAX_SLAB_BYTES = 1ull << 46;
+constexpr unsigned BDF_CHUNK_EVENTS = 32;      // input chunks in flight per host compress call
 
 struct DevBuf {
     void *p = nullptr;
@@ -60,10 +61,17 @@ struct bdf_ctx {
     int inflate_group = 16;                     // lanes per stream in inflate_kernel (BDF_INFLATE_GROUP)
     int inflate_mode = 0;                       // 0 = both engines, split by expansion ratio; 1 = lane groups only; 2 = lane per stream only (BDF_INFLATE_MODE)
     int inflate_split = 16;                     // expansion ratio from which a stream goes to the lane-group kernel (BDF_INFLATE_SPLIT)
-    int lane_cfg = 0;                           // direct-table bits of inflate_lane_kernel: 0 = (8, 7), 7 warps / SM; 1 = (9, 6), 5 warps / SM (BDF_LANE_CFG)
+    int lane_cfg = 0;                           // direct-table bits of inflate_lane_kernel: 0 = (8, 7), 7 warps / SM; 1 = (9, 6), 5 warps / SM; 2 = (8, 6), 8 warps / SM (BDF_LANE_CFG)
     int lane_warps_per_sm = 0;                  // cap on resident warps of inflate_lane_kernel, 0 = what fits (BDF_LANE_WARPS)
     bdf::DeflateScratch deflate_scratch;
-    DevBuf in, out, in_off, out_off, max_out, out_size, status, checksum, lane_scratch;
+    DevBuf in, out, in_off, out_off, max_out, out_size, status, checksum, lane_scratch, dense, dense_off;
+    void *h_stage[2] = {nullptr, nullptr};      // pinned: packing buffers of a scattered input
+    size_t h_stage_cap[2] = {0, 0};
+    void *h_result = nullptr;                   // pinned: dense result on its way to bound-spaced slots
+    size_t h_result_cap = 0;
+    cudaEvent_t ev_chunk[BDF_CHUNK_EVENTS] = {};
+    cudaEvent_t ev_stage[2] = {};
+    unsigned stage_no = 0;
     DevBuf u_in_off, u_tmp_off, u_size, u_status, u_flags, u_begin, u_tmp;     // chunked compression (units)
 };
 
@@ -174,6 +182,7 @@ template <int FORMAT>
 int launch_inflate_lane(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
 {
     if (ctx->lane_cfg == 1) return launch_inflate_lane_c<FORMAT, 9, 6>(ctx, a, s);
+    if (ctx->lane_cfg == 2) return launch_inflate_lane_c<FORMAT, 8, 6>(ctx, a, s);
     return launch_inflate_lane_c<FORMAT, 8, 7>(ctx, a, s);
 }
 
@@ -253,7 +262,7 @@ int bdf_ctx_create(int device, bdf_ctx **out)
         int v = atoi(e);
         if (v >= 1 && v <= 1032) ctx->inflate_split = v;
     }
-    if (const char *e = getenv("BDF_LANE_CFG")) ctx->lane_cfg = atoi(e) == 1 ? 1 : 0;
+    if (const char *e = getenv("BDF_LANE_CFG")) ctx->lane_cfg = atoi(e) >= 0 && atoi(e) <= 2 ? atoi(e) : 0;
     if (const char *e = getenv("BDF_LANE_WARPS")) ctx->lane_warps_per_sm = atoi(e) > 0 ? atoi(e) : 0;
     {
         // Device-to-host result copies per call.  Eight concurrent copies are best when one process
@@ -278,6 +287,8 @@ int bdf_ctx_create(int device, bdf_ctx **out)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming);
+    for (unsigned i = 0; i < BDF_CHUNK_EVENTS && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_stage[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counters, NUM_COUNTER_SLOTS * sizeof(unsigned long long));
     if (e == cudaSuccess) {
         bdf::crc_tables_init_kernel<<<1, 256, 0, ctx->stream>>>();
@@ -299,7 +310,7 @@ void bdf_ctx_destroy(bdf_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->in, &ctx->out, &ctx->in_off, &ctx->out_off, &ctx->max_out,
-                      &ctx->out_size, &ctx->status, &ctx->checksum, &ctx->lane_scratch, &ctx->u_in_off, &ctx->u_tmp_off,
+                      &ctx->out_size, &ctx->status, &ctx->checksum, &ctx->lane_scratch, &ctx->dense, &ctx->dense_off, &ctx->u_in_off, &ctx->u_tmp_off,
                       &ctx->u_size, &ctx->u_status, &ctx->u_flags, &ctx->u_begin, &ctx->u_tmp};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -313,6 +324,10 @@ void bdf_ctx_destroy(bdf_ctx *ctx)
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
+    for (unsigned i = 0; i < BDF_CHUNK_EVENTS; i++) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
+    for (int i = 0; i < 2; i++) if (ctx->ev_stage[i]) cudaEventDestroy(ctx->ev_stage[i]);
+    for (int i = 0; i < 2; i++) if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
+    if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -640,76 +655,240 @@ static int compress_chunked_locked(bdf_ctx *ctx, int level, int format, const ui
     return BDF_E_OK;
 }
 
-int bdf_compress_batch_host(bdf_ctx *ctx, int level, int format, const uint8_t *in, const uint64_t *in_off,
-                            size_t n, uint8_t *out, const uint64_t *out_off, uint64_t *out_size, int32_t *status)
+// ---- host compress calls.  One implementation behind three entry points (flat input + bound-spaced
+// output, flat input + dense output, scattered input + dense output):
+//   * the input goes to the device in chunks on a copy stream while the kernels of earlier chunks
+//     run (a scattered input is first packed into two pinned staging buffers, chunk by chunk);
+//   * the result is packed on the device (size scan + gather_kernel) and comes back as ONE copy of
+//     what was produced — not one copy per stream, and never the bound-sized slab.
+struct HostInput {
+    const uint8_t *flat;               // flat input, or
+    const uint8_t *const *ptrs;        // n scattered buffers
+    const uint64_t *off;               // n + 1 offsets into the (virtual) flat input
+};
+
+static int ensure_host(bdf_ctx *ctx, void *&p, size_t &cap, size_t bytes)
 {
-    if (!ctx) return BDF_E_ARG;
-    if (bad_format(format)) return fail(ctx, BDF_E_ARG, "unknown format");
-    if (level < 0) return fail(ctx, BDF_E_ARG, "negative level");
-    if (n == 0) return BDF_E_OK;
-    if (!in || !in_off || !out || !out_off || !out_size || !status) return fail(ctx, BDF_E_ARG, "null pointer");
-    if (n > 0xFFFFFFF0ull) return fail(ctx, BDF_E_ARG, "too many streams");
-    size_t in_bytes, out_bytes = 0;
+    if (cap >= bytes) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(ctx, BDF_E_NOMEM, "cudaHostAlloc", e);
+    cap = bytes;
+    return 0;
+}
+
+// Packs the bound-spaced slab into ctx->dense; leaves offsets (n + 1) in ctx->dense_off on the
+// device and in `dense_off` on the host (synchronises the stream).
+static int pack_result_locked(bdf_ctx *ctx, size_t n, uint64_t *dense_off, cudaStream_t s)
+{
+    int rc;
+    if ((rc = ensure(ctx, ctx->dense_off, (n + 1) * 8))) return rc;
+    bdf::size_scan_kernel<<<1, bdf::SCAN_THREADS, 0, s>>>((const uint64_t *)ctx->out_size.p, (uint64_t *)ctx->dense_off.p, (uint32_t)n);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dense_off, ctx->dense_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const size_t total = (size_t)dense_off[n];
+    if ((rc = ensure(ctx, ctx->dense, total + 16))) return rc;
+    bdf::GatherArgs ga{(const uint8_t *)ctx->out.p, (const uint64_t *)ctx->out_off.p, (const uint64_t *)ctx->out_size.p,
+                       (uint8_t *)ctx->dense.p, (const uint64_t *)ctx->dense_off.p, (uint32_t)n};
+    unsigned long long want = (n + bdf::GATHER_WARPS - 1) / bdf::GATHER_WARPS;
+    unsigned long long full = (unsigned long long)ctx->sm_count * 16;
+    bdf::gather_kernel<<<(unsigned)(want < full ? want : full), bdf::GATHER_WARPS * 32, 0, s>>>(ga);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// dense != nullptr: dense result (dense_cap bytes, offsets to dense_off[n + 1]); else the result is
+// scattered into the caller's bound-spaced slots out + out_off[i] and sizes go to out_size.
+static int compress_host_impl(bdf_ctx *ctx, int level, int format, const HostInput &hin, size_t n,
+                              uint8_t *dense, size_t dense_cap, uint64_t *dense_off,
+                              uint8_t *out, const uint64_t *out_off, uint64_t *out_size, int32_t *status)
+{
+    const uint64_t *in_off = hin.off;
     uint64_t max_len = 0;
-    for (size_t i = 0; i < n; i++)
+    for (size_t i = 0; i < n; i++) {
+        if (in_off[i] > in_off[i + 1]) return fail(ctx, BDF_E_ARG, "in_off is not ascending");
         if (in_off[i + 1] - in_off[i] > max_len) max_len = in_off[i + 1] - in_off[i];
+    }
+    if (in_off[n] > BDF_MAX_SLAB_BYTES) return fail(ctx, BDF_E_ARG, "input too large");
     // level 0 needs the unit path only above one chunk (the stored kernel handles any length)
     const bool chunked = max_len > (level == 0 ? 256u * 1024u : 65536u);
     // one lock for the whole call: the staging buffers of the ctx are shared by all callers
     std::lock_guard<std::mutex> g(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    {
-        CK(cudaSetDevice(ctx->device));
-        in_bytes = (size_t)in_off[n];
+    const size_t in_bytes = (size_t)in_off[n];
+    // device slab at the reference's bounds (src/batch.rs:39), 16-byte aligned slots
+    std::vector<uint64_t> slab_off(n);
+    size_t slab_bytes = 0;
+    for (size_t i = 0; i < n; i++) {
+        slab_off[i] = slab_bytes;
+        slab_bytes += (bdf_compress_bound(format, (size_t)(in_off[i + 1] - in_off[i])) + 15) & ~(size_t)15;
+    }
+    if (dense) {
+        if (overlaps(hin.flat, hin.flat ? in_bytes : 0, dense, dense_cap)) return fail(ctx, BDF_E_ARG, "Input and output buffers overlap");
+    } else {
+        size_t out_bytes = 0;
         for (size_t i = 0; i < n; i++) {
-            size_t e = (size_t)out_off[i] + bdf_compress_bound(format, (size_t)(in_off[i + 1] - in_off[i]));
-            if (e > out_bytes) out_bytes = e;
+            const uint64_t e = out_off[i] + bdf_compress_bound(format, (size_t)(in_off[i + 1] - in_off[i]));
+            if (e < out_off[i] || e > BDF_MAX_SLAB_BYTES) return fail(ctx, BDF_E_ARG, "out_off overflows");
+            if (e > out_bytes) out_bytes = (size_t)e;
         }
-        if (overlaps(in, in_bytes, out, out_bytes)) return fail(ctx, BDF_E_ARG, "Input and output buffers overlap");
-        int rc;
-        if ((rc = ensure(ctx, ctx->in, in_bytes + 8)) || (rc = ensure(ctx, ctx->out, out_bytes + 8)) ||
-            (rc = ensure(ctx, ctx->in_off, (n + 1) * 8)) || (rc = ensure(ctx, ctx->out_off, n * 8)) ||
-            (rc = ensure(ctx, ctx->out_size, n * 8)) || (rc = ensure(ctx, ctx->status, n * 4)))
-            return rc;
-        CK(cudaMemcpyAsync(ctx->in.p, in, in_bytes, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->in_off.p, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->out_off.p, out_off, n * 8, cudaMemcpyHostToDevice, s));
-        if (chunked) {
-            rc = compress_chunked_locked(ctx, level, format, in_off, n, s);
-            if (rc) return rc;
-        } else {
-            CK(cudaEventRecord(ctx->ev0, s));
+        if (overlaps(hin.flat, hin.flat ? in_bytes : 0, out, out_bytes)) return fail(ctx, BDF_E_ARG, "Input and output buffers overlap");
+    }
+    int rc;
+    if ((rc = ensure(ctx, ctx->in, in_bytes + 8)) || (rc = ensure(ctx, ctx->out, slab_bytes + 8)) ||
+        (rc = ensure(ctx, ctx->in_off, (n + 1) * 8)) || (rc = ensure(ctx, ctx->out_off, n * 8)) ||
+        (rc = ensure(ctx, ctx->out_size, n * 8)) || (rc = ensure(ctx, ctx->status, n * 4)))
+        return rc;
+    CK(cudaMemcpyAsync(ctx->in_off.p, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->out_off.p, slab_off.data(), n * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));                  // slab_off is read by the copy above; also orders the staging reuse below
+    // ---- input chunks: copy stream ahead of the kernels
+    const size_t CHUNK = 64u << 20;
+    if (hin.ptrs && (rc = ensure_host(ctx, ctx->h_stage[0], ctx->h_stage_cap[0], CHUNK)) ) return rc;
+    if (hin.ptrs && (rc = ensure_host(ctx, ctx->h_stage[1], ctx->h_stage_cap[1], CHUNK)) ) return rc;
+    cudaStream_t cs = ctx->copy_streams[0];
+    CK(cudaEventRecord(ctx->ev0, s));
+    unsigned chunk_no = 0;
+    // kernels for streams [a, b) once their bytes are on their way (event on the copy stream)
+    auto launch_range = [&](size_t a, size_t b) -> int {
+        cudaEvent_t ev = ctx->ev_chunk[chunk_no++ % BDF_CHUNK_EVENTS];
+        CK(cudaEventRecord(ev, cs));
+        CK(cudaStreamWaitEvent(s, ev, 0));
+        if (chunked || b <= a) return 0;
+        return compress_device_locked(ctx, level, format, (const uint8_t *)ctx->in.p,
+                                      (const uint64_t *)ctx->in_off.p + a, b - a, (uint8_t *)ctx->out.p,
+                                      (const uint64_t *)ctx->out_off.p + a, (uint64_t *)ctx->out_size.p + a,
+                                      (int32_t *)ctx->status.p + a, s);
+    };
+    if (hin.flat) {
+        size_t a = 0;
+        while (a < n) {
+            size_t b = a;
+            while (b < n && (b == a || in_off[b + 1] - in_off[a] <= CHUNK)) b++;
+            const size_t beg = (size_t)in_off[a], bytes = (size_t)in_off[b] - beg;
+            if (bytes) CK(cudaMemcpyAsync((uint8_t *)ctx->in.p + beg, hin.flat + beg, bytes, cudaMemcpyHostToDevice, cs));
+            if ((rc = launch_range(a, b))) return rc;
+            a = b;
+        }
+    } else {
+        // pack the buffers into the two pinned staging buffers in turn; a kernel starts for the
+        // streams that are complete after each buffer
+        size_t k = 0, koff = 0, launched = 0, dev_pos = 0;
+        while (k < n) {
+            const unsigned b = ctx->stage_no++ & 1u;
+            uint8_t *st = (uint8_t *)ctx->h_stage[b];
+            CK(cudaEventSynchronize(ctx->ev_stage[b]));           // the copy that read this buffer last
+            size_t fill = 0;
+            while (k < n) {
+                const size_t len = (size_t)(in_off[k + 1] - in_off[k]);
+                size_t cnt = len - koff;
+                if (cnt > CHUNK - fill) cnt = CHUNK - fill;
+                if (cnt) memcpy(st + fill, hin.ptrs[k] + koff, cnt);
+                fill += cnt;
+                koff += cnt;
+                if (koff < len) break;                            // buffer full in the middle of a stream
+                k++;
+                koff = 0;
+                if (fill == CHUNK) break;
+            }
+            if (fill) CK(cudaMemcpyAsync((uint8_t *)ctx->in.p + dev_pos, st, fill, cudaMemcpyHostToDevice, cs));
+            CK(cudaEventRecord(ctx->ev_stage[b], cs));
+            dev_pos += fill;
+            if (k > launched) {
+                if ((rc = launch_range(launched, k))) return rc;
+                launched = k;
+            }
         }
     }
-    int rc = BDF_E_OK;
-    if (!chunked)
-        rc = compress_device_locked(ctx, level, format, (const uint8_t *)ctx->in.p,
-                                    (const uint64_t *)ctx->in_off.p, n, (uint8_t *)ctx->out.p,
-                                    (const uint64_t *)ctx->out_off.p, (uint64_t *)ctx->out_size.p,
-                                    (int32_t *)ctx->status.p, s);
-    if (rc) return rc;
+    if (chunked) {
+        rc = compress_chunked_locked(ctx, level, format, in_off, n, s);
+        if (rc) return rc;
+    }
     CK(cudaEventRecord(ctx->ev1, s));
-    CK(cudaMemcpyAsync(out_size, ctx->out_size.p, n * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(status, ctx->status.p, n * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    // ---- result: pack on the device, one copy back
+    std::vector<uint64_t> tmp_off;
+    uint64_t *doff = dense_off;
+    if (!dense) { tmp_off.resize(n + 1); doff = tmp_off.data(); }
+    if ((rc = pack_result_locked(ctx, n, doff, s))) return rc;
     cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
-    // Copy back only what was produced: contiguous runs of streams are merged
-    // so that a 4 GiB bound-sized slab is not dragged over PCIe for a few MB.
-    size_t i = 0;
-    while (i < n) {
-        size_t beg = (size_t)out_off[i], end = beg + (size_t)out_size[i];
-        size_t j = i + 1;
-        // merge neighbours whose gap is small (cheaper than another copy call)
-        while (j < n && (size_t)out_off[j] >= end && (size_t)out_off[j] - end <= 4096) {
-            end = (size_t)out_off[j] + (size_t)out_size[j];
-            j++;
-        }
-        if (end > beg) CK(cudaMemcpyAsync(out + beg, (const uint8_t *)ctx->out.p + beg, end - beg,
-                                          cudaMemcpyDeviceToHost, s));
-        i = j;
+    const size_t total = (size_t)doff[n];
+    if (dense) {
+        if (total > dense_cap) return fail(ctx, BDF_E_ARG, "dense output buffer too small (needed size is in out_off[n])");
+        if (total) CK(cudaMemcpyAsync(dense, ctx->dense.p, total, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return BDF_E_OK;
     }
+    if ((rc = ensure_host(ctx, ctx->h_result, ctx->h_result_cap, total + 16))) return rc;
+    if (total) CK(cudaMemcpyAsync(ctx->h_result, ctx->dense.p, total, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    for (size_t i = 0; i < n; i++) {
+        const size_t sz = (size_t)(doff[i + 1] - doff[i]);
+        out_size[i] = sz;
+        if (sz) memcpy(out + out_off[i], (const uint8_t *)ctx->h_result + doff[i], sz);
+    }
     return BDF_E_OK;
+}
+
+static int compress_host_args(bdf_ctx *ctx, int level, int format, size_t n)
+{
+    if (bad_format(format)) return fail(ctx, BDF_E_ARG, "unknown format");
+    if (level < 0) return fail(ctx, BDF_E_ARG, "negative level");
+    if (n > 0xFFFFFFF0ull) return fail(ctx, BDF_E_ARG, "too many streams");
+    return 0;
+}
+
+int bdf_compress_batch_host(bdf_ctx *ctx, int level, int format, const uint8_t *in, const uint64_t *in_off,
+                            size_t n, uint8_t *out, const uint64_t *out_off, uint64_t *out_size, int32_t *status)
+{
+    if (!ctx) return BDF_E_ARG;
+    int rc = compress_host_args(ctx, level, format, n);
+    if (rc) return rc;
+    if (n == 0) return BDF_E_OK;
+    if (!in || !in_off || !out || !out_off || !out_size || !status) return fail(ctx, BDF_E_ARG, "null pointer");
+    HostInput hin{in, nullptr, in_off};
+    return compress_host_impl(ctx, level, format, hin, n, nullptr, 0, nullptr, out, out_off, out_size, status);
+}
+
+int bdf_compress_batch_host_dense(bdf_ctx *ctx, int level, int format, const uint8_t *in, const uint64_t *in_off,
+                                  size_t n, uint8_t *out, size_t out_cap, uint64_t *out_off, int32_t *status)
+{
+    if (!ctx) return BDF_E_ARG;
+    int rc = compress_host_args(ctx, level, format, n);
+    if (rc) return rc;
+    if (!out_off) return fail(ctx, BDF_E_ARG, "null pointer");
+    if (n == 0) { out_off[0] = 0; return BDF_E_OK; }
+    if (!in || !in_off || !out || !status) return fail(ctx, BDF_E_ARG, "null pointer");
+    HostInput hin{in, nullptr, in_off};
+    return compress_host_impl(ctx, level, format, hin, n, out, out_cap, out_off, nullptr, nullptr, nullptr, status);
+}
+
+int bdf_compress_batch_host_sg(bdf_ctx *ctx, int level, int format, const uint8_t *const *in_ptrs,
+                               const size_t *in_lens, size_t n, uint8_t *out, size_t out_cap, uint64_t *out_off,
+                               int32_t *status)
+{
+    if (!ctx) return BDF_E_ARG;
+    int rc = compress_host_args(ctx, level, format, n);
+    if (rc) return rc;
+    if (!out_off) return fail(ctx, BDF_E_ARG, "null pointer");
+    if (n == 0) { out_off[0] = 0; return BDF_E_OK; }
+    if (!in_ptrs || !in_lens || !out || !status) return fail(ctx, BDF_E_ARG, "null pointer");
+    std::vector<uint64_t> off(n + 1);
+    off[0] = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (in_lens[i] && !in_ptrs[i]) return fail(ctx, BDF_E_ARG, "null pointer");
+        if (overlaps(in_ptrs[i], in_lens[i], out, out_cap)) return fail(ctx, BDF_E_ARG, "Input and output buffers overlap");
+        off[i + 1] = off[i] + in_lens[i];
+        if (off[i + 1] < off[i]) return fail(ctx, BDF_E_ARG, "input too large");
+    }
+    HostInput hin{nullptr, in_ptrs, off.data()};
+    return compress_host_impl(ctx, level, format, hin, n, out, out_cap, out_off, nullptr, nullptr, nullptr, status);
 }
 
 // --------------------------------------------------------------------- units

@@ -48,4 +48,28 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) gather_kernel(GatherArgs a)
         warp_copy_bytes(a.dst + a.dst_off[i], a.src + a.src_off[i], a.size[i], lane);
 }
 
+// dst_off[0..n] = exclusive prefix sums of size[0..n) (one CTA; the batch sizes of this engine,
+// up to a few million streams, take microseconds)
+constexpr int SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(SCAN_THREADS) size_scan_kernel(const uint64_t *size, uint64_t *dst_off, uint32_t n)
+{
+    __shared__ uint64_t part[SCAN_THREADS];
+    const uint32_t per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
+    const uint32_t beg = threadIdx.x * per < n ? threadIdx.x * per : n;
+    const uint32_t end = beg + per < n ? beg + per : n;
+    uint64_t sum = 0;
+    for (uint32_t i = beg; i < end; i++) sum += size[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < SCAN_THREADS; d <<= 1) {
+        const uint64_t v = threadIdx.x >= (unsigned)d ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint64_t run = part[threadIdx.x] - sum;
+    for (uint32_t i = beg; i < end; i++) { dst_off[i] = run; run += size[i]; }
+    if (threadIdx.x == SCAN_THREADS - 1) dst_off[n] = part[SCAN_THREADS - 1];
+}
+
 }  // namespace bdf

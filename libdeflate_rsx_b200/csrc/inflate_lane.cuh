@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
     // flushed byte by byte, ever gets there).
     constexpr uint32_t NEAR = RING - 24;
     constexpr uint32_t COPY_MAX = RING - 56, DECODE_MAX = RING - 40;
+    constexpr uint32_t FLUSH_AT = 56;             // < COPY_MAX - 16: a lane that reaches it still has a round of room
     constexpr bool ADLER = FORMAT == BDF_ZLIB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LaneSmem<LTB, OTB> &sm = *reinterpret_cast<LaneSmem<LTB, OTB> *>(smem_raw);
@@ -484,30 +485,36 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                     }
                 }
             }
-            // ---- C: one complete 32-byte sector of the ring -> global memory
-            if (st == LS_RUN) {
-                const uint32_t mis = (flushed + rbias) & 31u;   // == (out + flushed) & 31
-                if (mis != 0) {
-                    // ragged head of a stream (or behind a stored block): byte by byte up to the boundary
-                    if (pos > flushed) {
-                        const uint32_t b = ring[(flushed + rbias) & MASK];
-                        out[flushed] = (uint8_t)b;
-                        if (ADLER) { sumA += b; sumB += (uint64_t)flushed * b; }
-                        flushed++;
+            // ---- C: complete 32-byte sectors of the ring -> global memory.  The section runs for the whole
+            // warp once a lane has FLUSH_AT bytes waiting (every second or third round) instead of
+            // every round for the few lanes that happen to have a sector ready.
+            if (__any_sync(BDF_FULL_MASK, st == LS_RUN && pos - flushed >= FLUSH_AT)) {
+                if (st == LS_RUN) {
+                    const uint32_t mis = (flushed + rbias) & 31u;   // == (out + flushed) & 31
+                    if (mis != 0) {
+                        // ragged head of a stream (or behind a stored block): byte by byte up to the boundary
+                        uint32_t k = 32u - mis;
+                        if (k > pos - flushed) k = pos - flushed;
+                        for (; k; k--) {
+                            const uint32_t b = ring[(flushed + rbias) & MASK];
+                            out[flushed] = (uint8_t)b;
+                            if (ADLER) { sumA += b; sumB += (uint64_t)flushed * b; }
+                            flushed++;
+                        }
+                    } else if (pos - flushed >= 32u) {
+                        const uint4 *rq = reinterpret_cast<const uint4 *>(ring + ((flushed + rbias) & MASK));
+                        const uint4 v0 = rq[0], v1 = rq[1];
+                        uint4 *dst = reinterpret_cast<uint4 *>(out + flushed);
+                        dst[0] = v0;
+                        dst[1] = v1;
+                        if (ADLER) {
+                            const uint32_t s0 = sum4(v0.x, v0.y, v0.z, v0.w), s1 = sum4(v1.x, v1.y, v1.z, v1.w);
+                            sumA += s0 + s1;
+                            sumB += (uint64_t)flushed * (s0 + s1) +
+                                    (16u * s1 + wsum4(v0.x, v0.y, v0.z, v0.w) + wsum4(v1.x, v1.y, v1.z, v1.w));
+                        }
+                        flushed += 32;
                     }
-                } else if (pos - flushed >= 32u) {
-                    const uint4 *rq = reinterpret_cast<const uint4 *>(ring + ((flushed + rbias) & MASK));
-                    const uint4 v0 = rq[0], v1 = rq[1];
-                    uint4 *dst = reinterpret_cast<uint4 *>(out + flushed);
-                    dst[0] = v0;
-                    dst[1] = v1;
-                    if (ADLER) {
-                        const uint32_t s0 = sum4(v0.x, v0.y, v0.z, v0.w), s1 = sum4(v1.x, v1.y, v1.z, v1.w);
-                        sumA += s0 + s1;
-                        sumB += (uint64_t)flushed * (s0 + s1) +
-                                (16u * s1 + wsum4(v0.x, v0.y, v0.z, v0.w) + wsum4(v1.x, v1.y, v1.z, v1.w));
-                    }
-                    flushed += 32;
                 }
             }
         }

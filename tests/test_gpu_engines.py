@@ -21,6 +21,7 @@ MODES = [
     {"BDF_INFLATE_MODE": "group", "BDF_INFLATE_GROUP": "32"},
     {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "0"},
     {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "1"},
+    {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "2"},
     {"BDF_INFLATE_MODE": "auto", "BDF_INFLATE_SPLIT": "16"},
     {"BDF_INFLATE_MODE": "auto", "BDF_INFLATE_SPLIT": "3"},
 ]
