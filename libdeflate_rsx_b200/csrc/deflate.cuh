@@ -11,6 +11,7 @@
 #include "deflate_common.cuh"
 #include "deflate_bt.cuh"
 #include "deflate_hc.cuh"
+#include "deflate_hcs.cuh"
 #include "deflate_l1.cuh"
 #include "gather.cuh"
 
@@ -19,7 +20,7 @@ namespace bdf {
 struct DeflateScratch {
     void *p = nullptr;
     size_t cap = 0;
-    bool l1_ready = false, hc_ready = false;
+    bool l1_ready = false, hc_ready = false, hcs_ready = false;
 };
 inline void deflate_scratch_free(DeflateScratch &s)
 {
@@ -168,6 +169,42 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
         if (a.size_only) deflate_l1_kernel<true, true><<<grid, L1_WARPS * 32, smem, s>>>(a);
         else if (big) deflate_l1_kernel<true><<<grid, L1_WARPS * 32, smem, s>>>(a);
         else deflate_l1_kernel<false><<<grid, L1_WARPS * 32, smem, s>>>(a);
+        *nlaunch = 1;
+        return cudaGetLastError();
+    }
+    static int hc_old = -1;
+    if (hc_old < 0) {
+        const char *env = getenv("BDF_HC_KERNEL");
+        hc_old = env && !strcmp(env, "old") ? 1 : 0;
+    }
+    if (a.level <= 9 && !big && !hc_old) {
+        // streams of at most 64 KiB: everything in shared memory, one 1024-thread CTA per SM
+        const size_t smem = sizeof(HcsSmem);
+        if (!scratch.hcs_ready) {
+            *why = "cudaFuncSetAttribute(deflate_hcs_kernel)";
+            e = cudaFuncSetAttribute(deflate_hcs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(deflate_hcs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            scratch.hcs_ready = true;
+            *why = nullptr;
+        }
+        const unsigned grid = a.n < (unsigned)sm_count ? a.n : (unsigned)sm_count;
+        const size_t need = HCS_SCRATCH_PER_CTA * (size_t)sm_count;
+        if (scratch.cap < need) {
+            if (scratch.p) cudaFree(scratch.p);
+            scratch.p = nullptr;
+            scratch.cap = 0;
+            *why = "cudaMalloc(deflate scratch)";
+            e = cudaMalloc(&scratch.p, need);
+            if (e != cudaSuccess) return e;
+            scratch.cap = need;
+            *why = nullptr;
+        }
+        a.scratch = scratch.p;
+        a.scratch_stride = HCS_SCRATCH_PER_CTA;
+        if (a.size_only) deflate_hcs_kernel<true><<<grid, HCS_THREADS, smem, s>>>(a);
+        else deflate_hcs_kernel<false><<<grid, HCS_THREADS, smem, s>>>(a);
         *nlaunch = 1;
         return cudaGetLastError();
     }
