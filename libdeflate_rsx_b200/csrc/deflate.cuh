@@ -77,6 +77,47 @@ __global__ void __launch_bounds__(L0_WARPS_PER_BLOCK * 32) deflate_stored_kernel
 }
 
 
+// ---- which hash-chain kernel a stream goes to (levels 2..9, at most 64 KiB).  deflate_hcs keeps a
+// whole stream in shared memory (one stream per SM) and searches every position; data that is one
+// long run or a short period — where nearly every step of the parse is a maximal match — is far
+// cheaper in deflate_hc, which searches only where the parse lands.  One warp per stream looks at
+// four places: the 8 bytes there must occur again within the 512 bytes in front of them, and the
+// 64 bytes there must repeat at that distance.  Three hits of four make the stream "runny".
+constexpr int CLASSIFY_WARPS = 8;
+__global__ void __launch_bounds__(CLASSIFY_WARPS * 32) deflate_classify_kernel(const uint8_t *in, const uint64_t *in_off,
+                                                                                uint32_t n, uint8_t *klass)
+{
+    const unsigned lane = lane_id();
+    for (uint32_t idx = blockIdx.x * CLASSIFY_WARPS + (threadIdx.x >> 5); idx < n; idx += gridDim.x * CLASSIFY_WARPS) {
+        const uint8_t *d = in + in_off[idx];
+        const uint64_t len = in_off[idx + 1] - in_off[idx];
+        unsigned hits = 0;
+        if (len >= 4096) {
+            for (unsigned k = 1; k <= 4; k++) {
+                const uint64_t p = len / 5 * k;                 // >= 819: 512 bytes in front, 64 behind
+                unsigned long long pat = 0;
+                for (int b = 0; b < 8; b++) pat |= (unsigned long long)d[p + b] << (8 * b);
+                unsigned best = 0xFFFFu;
+                for (unsigned o = 1 + lane; o <= 512; o += 32) {
+                    unsigned long long v = 0;
+                    for (int b = 0; b < 8; b++) v |= (unsigned long long)d[p - o + b] << (8 * b);
+                    if (v == pat && o < best) best = o;
+                }
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) {
+                    const unsigned t = __shfl_xor_sync(BDF_FULL_MASK, best, s);
+                    best = t < best ? t : best;
+                }
+                if (best != 0xFFFFu) {
+                    const bool same = d[p + lane] == d[p + lane - best] && d[p + 32 + lane] == d[p + 32 + lane - best];
+                    if (__all_sync(BDF_FULL_MASK, same)) hits++;
+                }
+            }
+        }
+        if (lane == 0) klass[idx] = hits >= 3 ? 1 : 0;
+    }
+}
+
 // Host-side dispatcher.  *why != nullptr with cudaSuccess means "unsupported".
 // ---- chunked streams: Compressor::compress, src/compress/mod.rs:699-772.  An input above 256 KiB
 // is cut into 256 KiB chunks, each compressed by a fresh compressor (units of the deflate kernels,
@@ -175,22 +216,35 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
     static int hc_old = -1;
     if (hc_old < 0) {
         const char *env = getenv("BDF_HC_KERNEL");
-        hc_old = env && !strcmp(env, "old") ? 1 : 0;
+        hc_old = env && !strcmp(env, "old") ? 1 : env && !strcmp(env, "new") ? 2 : 0;
     }
-    if (a.level <= 9 && !big && !hc_old) {
-        // streams of at most 64 KiB: everything in shared memory, one 1024-thread CTA per SM
-        const size_t smem = sizeof(HcsSmem);
+    if (a.level <= 9 && !big && hc_old != 1) {
+        // streams of at most 64 KiB: runs / short periods -> deflate_hc_kernel (searches where the parse
+        // lands), everything else -> deflate_hcs_kernel (everything in shared memory, one CTA per SM)
+        const size_t smem_s = sizeof(HcsSmem), smem_o = sizeof(HcSmem);
         if (!scratch.hcs_ready) {
             *why = "cudaFuncSetAttribute(deflate_hcs_kernel)";
-            e = cudaFuncSetAttribute(deflate_hcs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaFuncSetAttribute(deflate_hcs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
             if (e == cudaSuccess)
-                e = cudaFuncSetAttribute(deflate_hcs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                e = cudaFuncSetAttribute(deflate_hcs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(deflate_hc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_o);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(deflate_hc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_o);
             if (e != cudaSuccess) return e;
             scratch.hcs_ready = true;
             *why = nullptr;
         }
-        const unsigned grid = a.n < (unsigned)sm_count ? a.n : (unsigned)sm_count;
-        const size_t need = HCS_SCRATCH_PER_CTA * (size_t)sm_count;
+        static int hc_ctas = 0;
+        if (hc_ctas == 0) {
+            const char *env = getenv("BDF_HC_CTAS_PER_SM");
+            hc_ctas = env && atoi(env) > 0 ? atoi(env) : 8;
+        }
+        const unsigned old_full = (unsigned)sm_count * (unsigned)hc_ctas;
+        const size_t hcs_bytes = HCS_SCRATCH_PER_CTA * (size_t)sm_count;
+        const size_t old_bytes = HcChains<false>::SCRATCH_PER_CTA * (size_t)old_full;
+        const size_t klass_bytes = ((size_t)a.n + 255) & ~(size_t)255;
+        const size_t need = hcs_bytes + old_bytes + klass_bytes + 2 * sizeof(unsigned long long) + 256;
         if (scratch.cap < need) {
             if (scratch.p) cudaFree(scratch.p);
             scratch.p = nullptr;
@@ -201,11 +255,33 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
             scratch.cap = need;
             *why = nullptr;
         }
-        a.scratch = scratch.p;
+        uint8_t *base = static_cast<uint8_t *>(scratch.p);
+        uint8_t *klass = base + hcs_bytes + old_bytes;
+        unsigned long long *ctr2 = reinterpret_cast<unsigned long long *>(klass + klass_bytes);
+        const bool split = hc_old == 0;                  // BDF_HC_KERNEL=new: everything through deflate_hcs_kernel
+        if (split) {
+            unsigned long long want = ((unsigned long long)a.n + CLASSIFY_WARPS - 1) / CLASSIFY_WARPS;
+            unsigned long long full = (unsigned long long)sm_count * 8;
+            deflate_classify_kernel<<<(unsigned)(want < full ? want : full), CLASSIFY_WARPS * 32, 0, s>>>(a.in, a.in_off, a.n, klass);
+            e = cudaMemsetAsync(ctr2, 0, sizeof(unsigned long long), s);
+            if (e != cudaSuccess) return e;
+            DeflateArgs o = a;
+            o.klass = klass; o.want = 1;
+            o.work_counter = ctr2;
+            o.scratch = base + hcs_bytes;
+            o.scratch_stride = HcChains<false>::SCRATCH_PER_CTA;
+            const unsigned grid_o = a.n < old_full ? a.n : old_full;
+            if (a.size_only) deflate_hc_kernel<false, true><<<grid_o, HC_THREADS, smem_o, s>>>(o);
+            else deflate_hc_kernel<false><<<grid_o, HC_THREADS, smem_o, s>>>(o);
+            *nlaunch += 2;
+            a.klass = klass; a.want = 0;
+        }
+        const unsigned grid = a.n < (unsigned)sm_count ? a.n : (unsigned)sm_count;
+        a.scratch = base;
         a.scratch_stride = HCS_SCRATCH_PER_CTA;
-        if (a.size_only) deflate_hcs_kernel<true><<<grid, HCS_THREADS, smem, s>>>(a);
-        else deflate_hcs_kernel<false><<<grid, HCS_THREADS, smem, s>>>(a);
-        *nlaunch = 1;
+        if (a.size_only) deflate_hcs_kernel<true><<<grid, HCS_THREADS, smem_s, s>>>(a);
+        else deflate_hcs_kernel<false><<<grid, HCS_THREADS, smem_s, s>>>(a);
+        *nlaunch += 1;
         return cudaGetLastError();
     }
     if (a.level <= 9) {

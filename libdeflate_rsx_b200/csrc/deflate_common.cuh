@@ -32,6 +32,11 @@ struct DeflateArgs {
     // greedy parse, an empty input costs nothing).  final_block only matters at level 0 (:1073-1082).
     int size_only = 0;
     int final_block = 1;
+    // Levels 2..9, streams of at most 64 KiB: two kernels share a batch (deflate_hc.cuh for streams
+    // that are runs / short periods, deflate_hcs.cuh for the rest).  klass[i] is written by
+    // deflate_classify_kernel; a kernel takes the streams whose class equals `want` (NULL: all).
+    const uint8_t *klass = nullptr;
+    uint8_t want = 0;
 };
 constexpr unsigned UNIT_FINISH = 1u, UNIT_SYNC = 2u, UNIT_CAP5 = 4u;   // CAP5: 5 more bytes of room (DeflateEncoder, src/stream.rs:66-69)
 __host__ __device__ inline uint64_t unit_cap(uint64_t len, unsigned flags) { return len + (len / 65535 + 1) * 5 + 10 + ((flags & 4u) ? 5 : 0); }
@@ -375,6 +380,116 @@ __device__ void make_huffman_code_serial(unsigned num_syms, unsigned max_len, co
             if (l) a[s] = __brev(next[l]++) >> (32 - l);
         }
     }
+}
+
+
+// The same code construction by a whole CTA (all threads call it; it contains barriers).  The
+// order the reference's counting sort + overflow-bucket sort produces is simply ascending
+// (frequency, symbol) over the used symbols, so every symbol finds its slot by counting the
+// symbols that come before it; the in-place tree build and the depth pass stay with one thread
+// (they are chains of dependent steps), code lengths and codewords are assigned by all threads
+// again.  Same results as make_huffman_code_serial, bit for bit.
+//   a[] / lens[] as above; ctl: 20 words of shared scratch.
+__device__ void make_huffman_code_cta(unsigned num_syms, unsigned max_len, const uint32_t *freqs,
+                                      uint8_t *lens, uint32_t *a, uint32_t *ctl)
+{
+    const uint32_t SYM_MASK = 1023u, FREQ_MASK = ~1023u;
+    const unsigned tid = threadIdx.x;
+    if (tid == 0) ctl[16] = 0;
+    __syncthreads();
+    uint32_t f = 0;
+    if (tid < num_syms) {
+        f = freqs[tid];
+        if (f) {
+            unsigned rank = 0;
+            for (unsigned t = 0; t < num_syms; t++) {
+                const uint32_t g = freqs[t];
+                rank += (g != 0 && (g < f || (g == f && t < tid))) ? 1u : 0u;
+            }
+            a[rank] = tid | (f << 10);
+            atomicAdd(&ctl[16], 1u);
+        } else {
+            lens[tid] = 0;
+        }
+    }
+    __syncthreads();
+    const unsigned used = ctl[16];
+    if (used < 2) {
+        if (tid == 0) {
+            unsigned sym = used ? (a[0] & SYM_MASK) : 0;
+            unsigned nz = sym ? sym : 1;
+            a[0] = 0; lens[0] = 1;
+            a[nz] = 1; lens[nz] = 1;
+        }
+        __syncthreads();
+        return;
+    }
+    if (tid == 0) {
+        {
+            const unsigned last = used - 1;
+            unsigned i = 0, b = 0, e = 0;
+            while (e < last) {
+                uint32_t nf;
+                if (i < last && (b == e || (a[i + 1] & FREQ_MASK) <= (a[b] & FREQ_MASK))) {
+                    nf = (a[i] & FREQ_MASK) + (a[i + 1] & FREQ_MASK);
+                    i += 2;
+                } else if (b + 2 <= e && (i > last || (a[b + 1] & FREQ_MASK) < (a[i] & FREQ_MASK))) {
+                    nf = (a[b] & FREQ_MASK) + (a[b + 1] & FREQ_MASK);
+                    a[b] = (e << 10) | (a[b] & SYM_MASK);
+                    a[b + 1] = (e << 10) | (a[b + 1] & SYM_MASK);
+                    b += 2;
+                } else {
+                    nf = (a[i] & FREQ_MASK) + (a[b] & FREQ_MASK);
+                    a[b] = (e << 10) | (a[b] & SYM_MASK);
+                    i += 1;
+                    b += 1;
+                }
+                a[e] = nf | (a[e] & SYM_MASK);
+                e++;
+            }
+        }
+        uint32_t len_counts[16];
+#pragma unroll
+        for (int l = 0; l < 16; l++) len_counts[l] = 0;
+        const unsigned root = used - 2;
+        len_counts[1] = 2;
+        a[root] &= SYM_MASK;
+        for (int node = (int)root - 1; node >= 0; node--) {
+            unsigned parent = a[node] >> 10;
+            unsigned depth = (a[parent] >> 10) + 1;
+            a[node] = (a[node] & SYM_MASK) | (depth << 10);
+            if (depth >= max_len) {
+                depth = max_len - 1;
+                while (len_counts[depth] == 0) depth--;
+            }
+            len_counts[depth]--;
+            len_counts[depth + 1] += 2;
+        }
+#pragma unroll
+        for (int l = 0; l < 16; l++) ctl[l] = len_counts[l];
+    }
+    __syncthreads();
+    // sorted position i gets the longest lengths first
+    if (tid < used) {
+        unsigned acc = 0, L = 0;
+        for (unsigned l = max_len; l >= 1; l--) {
+            acc += ctl[l];
+            if (L == 0 && tid < acc) L = l;
+        }
+        lens[a[tid] & SYM_MASK] = (uint8_t)L;
+    }
+    __syncthreads();
+    if (tid < num_syms) {
+        const unsigned l = lens[tid];
+        if (l) {
+            uint32_t nx = 0;                                 // first codeword of length l
+            for (unsigned k = 2; k <= l; k++) nx = (nx + ctl[k - 1]) << 1;
+            unsigned rank = 0;
+            for (unsigned t = 0; t < tid; t++) rank += lens[t] == l ? 1u : 0u;
+            a[tid] = __brev(nx + rank) >> (32 - l);
+        }
+    }
+    __syncthreads();
 }
 
 }  // namespace bdf

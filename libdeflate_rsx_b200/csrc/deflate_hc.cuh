@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(HC_THREADS) deflate_hc_kernel(DeflateArgs a)
         __syncthreads();
         const unsigned long long idx = s_idx;
         if (idx >= a.n) break;
+        if (a.klass && a.klass[idx] != a.want) continue;       // the other kernel's stream
         const uint8_t *in = a.in + a.in_off[idx];
         const uint64_t len64 = a.in_off[idx + 1] - a.in_off[idx];
         uint8_t *out = SIZE ? nullptr : a.out + a.out_off[idx];

@@ -98,7 +98,7 @@ struct __align__(16) HcsSmem {
     uint16_t seg_entry[HCS_NSEG + 8], grp_entry[HCS_NGRP + 1];
     uint32_t scan_tmp[8];
     // control words (written by one thread, read by all after a barrier)
-    uint32_t c_next_entry, c_pc, c_rec_at_pc, c_win_rec, c_win_obs, c_split;
+    uint32_t c_next_entry, c_pc, c_rec_at_pc, c_win_rec, c_win_obs, c_split, c_search_next;
     // bit sink of the CTA
     uint32_t sink_bits;            // bits pending in enc.stage (after a round: < 8)
     uint32_t sink_carry;           // those bits (the staging buffer itself is overlaid between blocks)
@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_hcs_kernel(DeflateArgs
         __syncthreads();
         const unsigned long long idx = s_idx;
         if (idx >= a.n) break;
+        if (a.klass && a.klass[idx] != a.want) continue;       // the other kernel's stream
         const uint8_t *gin = a.in + a.in_off[idx];
         const uint64_t len64 = a.in_off[idx + 1] - a.in_off[idx];
         uint8_t *out = SIZE ? nullptr : a.out + a.out_off[idx];
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_hcs_kernel(DeflateArgs
         for (uint32_t i = tid; i < 288; i += HCS_THREADS) sm.litlen_freq[i] = 0;
         if (tid < 32) sm.offset_freq[tid] = 0;
         if (tid < 14) { sm.new_obs[tid] = 0; sm.obs[tid] = 0; }
-        if (tid == 0) { sm.num_new = 0; sm.num_obs = 0; }
+        if (tid == 0) { sm.num_new = 0; sm.num_obs = 0; sm.c_search_next = 0; }
         __syncthreads();
 
         // ================================================= phase 3: windows
@@ -361,15 +362,22 @@ __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_hcs_kernel(DeflateArgs
         while (more) {
             const uint32_t wvalid = len - entry < HCS_W ? len - entry : HCS_W;      // positions parsed in this window
             const uint32_t nsearch = len - entry < HCS_SEARCH ? len - entry : HCS_SEARCH;
-            // ---- search: every warp takes a contiguous range, every lane walks one chain at a time
+            // ---- search: warps take chunks of 32 positions from a counter; every lane walks one chain at a
+            // time and takes the next position of the chunk as soon as it is done
             {
-                const uint32_t per = (nsearch + HCS_WARPS - 1) / HCS_WARPS;
-                uint32_t next = warp * per < nsearch ? warp * per : nsearch;
-                const uint32_t range_end = next + per < nsearch ? next + per : nsearch;
-                bool active = false;
+                uint32_t next = 0, range_end = 0;
+                bool active = false, exhausted = false;
                 uint32_t p = 0, cur = 0, best = 0, boff = 0, depth = 0, first = 0, room = 0, src4 = 0, tb = 0;
                 bool can4 = false;
                 for (;;) {
+                    if (next >= range_end && !exhausted) {  // uniform: take the next chunk
+                        uint32_t c = 0;
+                        if (lane == 0) c = atomicAdd(&sm.c_search_next, 32u);
+                        c = __shfl_sync(BDF_FULL_MASK, c, 0);
+                        next = c < nsearch ? c : nsearch;
+                        range_end = c + 32u < nsearch ? c + 32u : nsearch;
+                        exhausted = c + 32u >= nsearch;
+                    }
                     const unsigned idle = __ballot_sync(BDF_FULL_MASK, !active);
                     if (idle && next < range_end) {
                         if (!active) {
@@ -390,7 +398,7 @@ __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_hcs_kernel(DeflateArgs
                         next += __popc(idle);
                     }
                     if (!__any_sync(BDF_FULL_MASK, active)) {
-                        if (next >= range_end) break;
+                        if (next >= range_end && exhausted) break;
                         continue;
                     }
                     if (active) {
@@ -463,7 +471,7 @@ __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_hcs_kernel(DeflateArgs
             if (tid < HCS_NGRP + 1) sm.grp_entry[tid] = (uint16_t)HCS_NONE;
             for (uint32_t i = tid; i < 320; i += HCS_THREADS) { sm.freq_a[i] = 0; sm.freq_b[i] = 0; }
             if (tid < 14) { sm.obs_a[tid] = 0; sm.obs_b[tid] = 0; }
-            if (tid == 0) { sm.cnt_a = 0; sm.cnt_b = 0; sm.c_pc = 0xFFFFFFFFu; sm.c_rec_at_pc = 0; sm.c_split = 0; }
+            if (tid == 0) { sm.cnt_a = 0; sm.cnt_b = 0; sm.c_pc = 0xFFFFFFFFu; sm.c_rec_at_pc = 0; sm.c_split = 0; sm.c_search_next = 0; }
             __syncthreads();
             // ---- P2: one thread per segment, backwards: exit and number of steps from every entry
             if (tid < HCS_NSEG) {
@@ -673,10 +681,11 @@ __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_hcs_kernel(DeflateArgs
                 // ---------------------------------------------- one block: codes, header, symbols
                 __syncthreads();
                 unsigned nlit_syms = 0, noff_syms = 0, npre = 0, nitems = 0;
+                if (tid == 0) sm.litlen_freq[256]++;
+                __syncthreads();
+                make_huffman_code_cta(288, 14, sm.litlen_freq, sm.litlen_len, sm.enc.litlen_code, sm.enc.scratch);
+                make_huffman_code_cta(32, 15, sm.offset_freq, sm.offset_len, sm.enc.offset_code, sm.enc.scratch);
                 if (tid == 0) {
-                    sm.litlen_freq[256]++;
-                    make_huffman_code_serial(288, 14, sm.litlen_freq, sm.litlen_len, sm.enc.litlen_code, sm.enc.scratch);
-                    make_huffman_code_serial(32, 15, sm.offset_freq, sm.offset_len, sm.enc.offset_code, sm.enc.scratch);
                     HcsHeaderView hv{sm.litlen_len, sm.offset_len, sm.enc.hdr_lens, sm.enc.hdr_items, sm.enc.pre_freq,
                                      sm.enc.pre_code, sm.enc.pre_len, sm.enc.scratch};
                     hc_prepare_header(hv, nlit_syms, noff_syms, npre, nitems);
