@@ -294,7 +294,8 @@ def compress_section(env, level, n, steps, e2e_steps, cpu_sample, cpu_seconds, w
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
-    kname = "bdf::deflate_l1_kernel" if level == 1 else "bdf::deflate_hc_kernel" if level <= 9 else "bdf::deflate_bt_kernel"
+    kname = ("bdf::deflate_l1_kernel" if level == 1 else "bdf::deflate_hc_kernel (corpus A is periodic: the classifier "
+             "sends it there)" if level <= 9 else "bdf::deflate_nos_kernel")
     sec = {
         "workload": f"compress {n} x 64 KiB of corpus A (gen_bench) per GPU at level {level}, raw DEFLATE; "
                     + ("byte-identical to the oracle" if level <= 9 else "total size <= 1.005 x the oracle's, zlib round trip"),
@@ -385,6 +386,31 @@ def pipeline_section(env, n, level, steps, e2e_steps, cpu_sample, cpu_seconds, w
         dist.all_reduce(cb, op=dist.ReduceOp.SUM)
     tc, tp, td, tall = [float(x) for x in tt.tolist()]
     ub = world * n * STREAM
+    # optional last step: the packed compressed shards of all ranks to one device over
+    # NVLink (NCCL gather of equally padded buffers; sizes travel first) — timed separately
+    gather_ms = None
+    if world > 1:
+        mx = torch.tensor([comp_bytes], dtype=torch.int64, device=dev)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        pad = (int(mx.item()) + 255) // 256 * 256
+        send = d_dense[:pad]
+        rank = dist.get_rank()
+        sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)] if rank == 0 else None
+        recv = [torch.empty(pad, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(2):
+            env["barrier"]()
+            g0.record(stream)
+            dist.gather(torch.tensor([comp_bytes], dtype=torch.int64, device=dev), sizes, dst=0)
+            dist.gather(send, recv, dst=0)
+            g1.record(stream)
+            torch.cuda.synchronize(dev)
+        gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+        gather_ms = float(gt.item())
+        if rank == 0:
+            assert int(sizes[world - 1].item()) > 0 and bool((recv[0][:comp_bytes] == d_dense[:comp_bytes]).all())
+        del recv, send
     del d_slab, d_dense, d_out, d_plain
     torch.cuda.empty_cache()
 
@@ -437,9 +463,11 @@ def pipeline_section(env, n, level, steps, e2e_steps, cpu_sample, cpu_seconds, w
         "value": ub / (tall * 1e-3) / 1e9, "pipeline": ub / (tall * 1e-3) / 1e9, "compress": ub / (tc * 1e-3) / 1e9,
         "decompress": ub / (td * 1e-3) / 1e9, "compress_ms": tc, "decompress_ms": td, "pack_ms": tp,
         "ratio": ub / cbytes, "gpu_launches_per_step": int(launches_per_step),
-        "roofline": roofline("bdf::deflate_hc_kernel + bdf::inflate_lane_kernel / inflate_kernel (whole pipeline)",
+        "gather_to_rank0_ms": gather_ms,
+        "pipeline_with_gather": (ub / ((tall + gather_ms) * 1e-3) / 1e9) if gather_ms is not None else None,
+        "roofline": roofline("bdf::deflate_hcs_kernel / deflate_hc_kernel + bdf::inflate_lane_kernel / inflate_kernel (whole pipeline)",
                              2 * (n * STREAM + comp_bytes), tall, n, "mixed_pipeline"),
-        "roofline_compress": roofline("bdf::deflate_hc_kernel", n * STREAM + comp_bytes, tc, n, f"deflate_l{level}_corpusB"),
+        "roofline_compress": roofline("bdf::deflate_hcs_kernel (+ deflate_hc_kernel for runs / short periods)", n * STREAM + comp_bytes, tc, n, f"deflate_l{level}_corpusB"),
         "roofline_decompress": roofline("bdf::inflate_lane_kernel + bdf::inflate_kernel", n * STREAM + comp_bytes, td, n, "inflate_corpusB"),
         "e2e": {"value": ub / (ec + ed) / 1e9, "compress": ub / ec / 1e9, "decompress": ub / ed / 1e9, "unit": "GB/s",
                 "steps": e2e_steps, "h2d_bytes_per_step": ubytes + comp_bytes + (4 * n + 2) * 8,

@@ -1,0 +1,54 @@
+"""Levels 10..12 (near-optimal tier): device-resident throughput per corpus kind and the batch's
+compressed size against the oracle's (tolerance 0.5 %); every distinct stream must inflate."""
+import ctypes as C
+import sys
+import zlib
+
+sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
+import numpy as np
+import torch
+
+import corpus
+import oracle_lib as o
+import libdeflate_rsx_b200 as b
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 2368
+dev = torch.device("cuda", 0)
+stream = torch.cuda.Stream(dev)
+torch.cuda.set_stream(stream)
+ctx = b.Context(0)
+D = 16
+GEN = {"text": corpus.text_stream, "mixedB": corpus.corpus_b_stream, "corpusA": lambda k: corpus.corpus_a_stream(k % 16),
+       "binary": corpus.binary_stream, "lowent": corpus.lowentropy_stream}
+n = n // D * D
+for kind in ("text", "mixedB", "binary", "lowent", "corpusA"):
+    plain = [GEN[kind](k) for k in range(D)]
+    d_in = torch.from_numpy(np.frombuffer(b"".join(plain), dtype=np.uint8).copy()).to(dev).repeat(n // D)
+    d_off = torch.arange(n + 1, dtype=torch.int64, device=dev) * 65536
+    bound = b.compress_bound(0, 65536)
+    d_out = torch.empty(n * bound, dtype=torch.uint8, device=dev)
+    d_ooff = torch.arange(n, dtype=torch.int64, device=dev) * bound
+    d_size = torch.zeros(n, dtype=torch.int64, device=dev)
+    d_stat = torch.zeros(n, dtype=torch.int32, device=dev)
+    for lvl in (10, 11, 12):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        best = None
+        for it in range(2):
+            d_stat.fill_(-1)
+            ev[0].record(stream)
+            ctx.check(ctx._lib.bdf_compress_batch_device(ctx.handle, lvl, 0, d_in.data_ptr(), d_off.data_ptr(), n, d_out.data_ptr(),
+                                                         d_ooff.data_ptr(), d_size.data_ptr(), d_stat.data_ptr(), C.c_void_p(stream.cuda_stream)))
+            ev[1].record(stream)
+            torch.cuda.synchronize(dev)
+            ms = ev[0].elapsed_time(ev[1])
+            best = ms if best is None or ms < best else best
+        sizes = d_size.cpu().numpy()
+        stat = d_stat.cpu().numpy()
+        ok = (stat == 0).all()
+        tot_g = tot_o = 0
+        for k in range(D):
+            got = d_out[k * bound:k * bound + int(sizes[k])].cpu().numpy().tobytes()
+            ok = ok and zlib.decompress(got, -15) == plain[k]
+            tot_g += len(got); tot_o += len(o.compress(plain[k], lvl))
+        print(f"{kind:8s} L{lvl}: {n * 65536 / best / 1e6:7.2f} GB/s  ms {best:8.1f}  size vs oracle {tot_g / tot_o:.4f} "
+              f"({tot_g} / {tot_o})  {'ok' if ok else 'BAD'}", flush=True)

@@ -20,7 +20,7 @@ namespace bdf {
 struct DeflateScratch {
     void *p = nullptr;
     size_t cap = 0;
-    bool l1_ready = false, hc_ready = false, hcs_ready = false;
+    bool l1_ready = false, hc_ready = false, hcs_ready = false, nos_ready = false;
 };
 inline void deflate_scratch_free(DeflateScratch &s)
 {
@@ -326,6 +326,40 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
         else if (a.size_only) deflate_hc_kernel<false, true><<<grid, HC_THREADS, smem, s>>>(a);
         else if (big) deflate_hc_kernel<true><<<grid, HC_THREADS, smem, s>>>(a);
         else deflate_hc_kernel<false><<<grid, HC_THREADS, smem, s>>>(a);
+        *nlaunch = 1;
+        return cudaGetLastError();
+    }
+    static int no_old = -1;
+    if (no_old < 0) {
+        const char *env = getenv("BDF_NO_KERNEL");
+        no_old = env && !strcmp(env, "old") ? 1 : 0;
+    }
+    if (!big && !a.size_only && !no_old) {
+        // levels 10..12, streams of at most 64 KiB: the near-optimal parser on the shared-memory
+        // hash-chain machinery (size within 0.5 % of the reference's, not its bytes)
+        const size_t smem = sizeof(HcsSmem);
+        if (!scratch.nos_ready) {
+            *why = "cudaFuncSetAttribute(deflate_nos_kernel)";
+            e = cudaFuncSetAttribute(deflate_nos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            scratch.nos_ready = true;
+            *why = nullptr;
+        }
+        const unsigned grid = a.n < (unsigned)sm_count ? a.n : (unsigned)sm_count;
+        const size_t need = NOS_SCRATCH_PER_CTA * (size_t)sm_count;
+        if (scratch.cap < need) {
+            if (scratch.p) cudaFree(scratch.p);
+            scratch.p = nullptr;
+            scratch.cap = 0;
+            *why = "cudaMalloc(deflate scratch)";
+            e = cudaMalloc(&scratch.p, need);
+            if (e != cudaSuccess) return e;
+            scratch.cap = need;
+            *why = nullptr;
+        }
+        a.scratch = scratch.p;
+        a.scratch_stride = NOS_SCRATCH_PER_CTA;
+        deflate_nos_kernel<<<grid, HCS_THREADS, smem, s>>>(a);
         *nlaunch = 1;
         return cudaGetLastError();
     }

@@ -77,6 +77,15 @@ struct HcsEncode {                 // live while a block is encoded
     uint32_t warp_tot[HCS_WARPS];
 };
 
+constexpr uint32_t HCS_DP_CHUNK = 504;                   // positions whose match lists are staged at a time (multiple of 3)
+struct HcsDp {                     // live while the near-optimal parser runs its cost pass over a block
+    uint32_t ring[512];            // cost to the end of the block for the 512 positions behind the current one
+    uint32_t lst[HCS_DP_CHUNK * 8];    // match lists of the chunk (8 entries per position; 16-byte aligned)
+    uint32_t ch[HCS_DP_CHUNK];         // choices of the chunk
+    uint8_t lit_cost[256], len_cost[260], slot_cost[32];
+};
+static_assert(offsetof(HcsDp, lst) % 16 == 0, "the lists are staged with 16-byte copies");
+
 struct __align__(16) HcsSmem {
     union {
         uint8_t in[65536 + 32];    // phase 2: the stream (zero padded)
@@ -87,6 +96,7 @@ struct __align__(16) HcsSmem {
         HcsWindow w;
         HcsInsert ins;
         HcsEncode enc;
+        HcsDp dp;
     };
     // block state (names shared with HcSmem: hc_should_end / hc_prepare_header run unchanged)
     uint32_t litlen_freq[288], offset_freq[32];          // current block, symbols of finished windows
@@ -222,6 +232,558 @@ struct HcsHeaderView {
     uint32_t *scratch;
 };
 
+// ---- the pieces of a stream's life, shared by the greedy / lazy kernel and the near-optimal one.
+// All of them are called by every thread of the CTA (they contain barriers).
+struct HcsStream {                 // uniform per stream
+    const uint8_t *gin;            // the stream in global memory
+    uint32_t len;
+    uint32_t gmis;                 // gin & 3
+    const uint32_t *gw;            // aligned words that hold the stream
+    __device__ __forceinline__ void set(const uint8_t *p, uint32_t n)
+    {
+        gin = p; len = n;
+        gmis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+        gw = reinterpret_cast<const uint32_t *>(p - gmis);
+    }
+    // 4 bytes of the stream at p (only words that hold a byte of the stream are touched)
+    __device__ __forceinline__ uint32_t g32(uint32_t p) const
+    {
+        const uint32_t q = p + gmis, k = q >> 2, sh = 8u * (q & 3u);
+        const uint32_t w0 = __ldg(gw + k);
+        if (sh == 0) return w0;
+        const uint32_t w1 = (k + 1) * 4u < len + gmis ? __ldg(gw + k + 1) : 0u;
+        return __funnelshift_r(w0, w1, sh);
+    }
+};
+
+// phase 1: chains of the whole stream (head + link)
+__device__ __forceinline__ void hcs_build_chains(HcsSmem &sm, const HcsStream &st)
+{
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t len = st.len;
+    auto g32 = [&](uint32_t p) { return st.g32(p); };
+    for (uint32_t i = tid; i < 32768 / 8; i += HCS_THREADS) reinterpret_cast<uint4 *>(sm.head)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    for (uint32_t i = tid; i < 65536 / 8; i += HCS_THREADS) reinterpret_cast<uint4 *>(sm.link)[i] = make_uint4(0, 0, 0, 0);
+    uint32_t l_head = 0, l_tail = 0;       // inserting warps: ring indices into their list (uniform per warp)
+    for (uint32_t b0 = 0; b0 < len; b0 += HCS_IBLK) {
+        __syncthreads();
+        for (uint32_t k = tid; k < HCS_INS_WARPS * (HCS_IBLK / 32); k += HCS_THREADS) (&sm.ins.cls[0][0])[k] = 0;
+        __syncthreads();
+        // (i) hash of every position of the round, and one bit in the row of the warp that will link
+        // it; the last two positions of a stream are never inserted
+        for (uint32_t k = tid; k < HCS_IBLK; k += HCS_THREADS) {
+            const uint32_t p = b0 + k;
+            if (p + 3 <= len) {
+                const uint32_t h = hash3(g32(p) & 0xFFFFFFu);
+                sm.ins.hbuf[k] = (uint16_t)h;
+                atomicOr(&sm.ins.cls[h & (HCS_INS_WARPS - 1)][k >> 5], 1u << (k & 31u));
+            }
+        }
+        __syncthreads();
+        // (ii) warp w links the positions whose hash is w modulo 16, in ascending order: it
+        // collects them from its bit row (8 positions per lane and step) and links 32 at a time.
+        // Chains of different hash values never touch, so the warps do not wait for one another.
+        if (warp < HCS_INS_WARPS) {
+            uint16_t *list = sm.ins.list[warp];
+            const uint32_t nblk = len - b0 < HCS_IBLK ? len - b0 : HCS_IBLK;
+            auto link_some = [&](uint32_t have) {
+                const bool ok = lane < have;
+                uint32_t k = 0, h = 0x10000u + lane;          // unique key for idle lanes
+                if (ok) { k = list[(l_head + lane) % HCS_LIST]; h = sm.ins.hbuf[k]; }
+                const uint32_t p = b0 + k;
+                const unsigned peers = __match_any_sync(BDF_FULL_MASK, h);
+                const unsigned lower = peers & lanemask_lt();
+                const uint32_t peer_pos = __shfl_sync(BDF_FULL_MASK, p, lower ? 31 - __clz(lower) : 0);
+                if (ok) {
+                    const uint32_t prev = lower ? peer_pos : (uint32_t)sm.head[h];
+                    sm.link[p] = (!lower && prev == HCS_NONE) ? (uint16_t)0 : (uint16_t)(p - prev);
+                }
+                __syncwarp();
+                if (ok && (peers >> lane) == 1u) sm.head[h] = (uint16_t)p;
+                __syncwarp();
+                l_head += have;
+            };
+            for (uint32_t s0 = 0; s0 < nblk; s0 += 256) {
+                uint32_t mine = (sm.ins.cls[warp][(s0 >> 5) + (lane >> 2)] >> (8u * (lane & 3u))) & 0xFFu;
+                const uint32_t cnt = __popc(mine);
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(BDF_FULL_MASK, incl, d);
+                    if (lane >= (unsigned)d) incl += t;
+                }
+                uint32_t at = l_tail + incl - cnt;
+                while (mine) {
+                    const uint32_t k = __ffs(mine) - 1;
+                    mine &= mine - 1;
+                    list[at % HCS_LIST] = (uint16_t)(s0 + 8 * lane + k);    // position inside the round
+                    at++;
+                }
+                l_tail += __shfl_sync(BDF_FULL_MASK, incl, 31);
+                __syncwarp();
+                while (l_tail - l_head >= 32u) link_some(32u);
+            }
+            while (l_tail != l_head) link_some(l_tail - l_head < 32u ? l_tail - l_head : 32u);   // the buffer is rewritten next round
+        }
+    }
+    __syncthreads();
+}
+
+// phase 2: the stream moves into shared memory (over the head table), zero padded
+__device__ __forceinline__ void hcs_stage_input(HcsSmem &sm, const HcsStream &st)
+{
+    const unsigned tid = threadIdx.x;
+    const uint32_t len = st.len;
+    auto g32 = [&](uint32_t p) { return st.g32(p); };
+    {
+        uint32_t *iw = reinterpret_cast<uint32_t *>(sm.in);
+        const uint32_t nw = (len + 3) >> 2;
+        for (uint32_t k = tid; k < (65536 + 32) / 4; k += HCS_THREADS) {
+            uint32_t v = 0;
+            if (k < nw) {
+                v = g32(4 * k);
+                if (4 * k + 4 > len) v &= 0xFFFFFFFFu >> (8 * (4 * k + 4 - len));     // zero padding behind the stream
+            }
+            iw[k] = v;
+        }
+    }
+}
+
+// find_match for the positions [entry, entry + nsearch): results to sm.w.res[position - entry].
+// LISTS: every improvement along the chain is also kept — up to HCS_NLIST (len | offset << 16)
+// entries of strictly increasing length per position in lists[position * HCS_NLIST ..] (global), the
+// match list the near-optimal parser relaxes (find_matches, src/compress/matchfinder.rs:1283-1296).
+constexpr uint32_t HCS_NLIST = 8;
+template <bool LISTS>
+__device__ __forceinline__ void hcs_search(HcsSmem &sm, uint32_t len, const HcParams &prm, uint32_t entry, uint32_t nsearch,
+                                           uint32_t *lists)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    // ---- search: warps take chunks of 32 positions from a counter; every lane walks one chain at a
+    // time and takes the next position of the chunk as soon as it is done
+    {
+        uint32_t next = 0, range_end = 0;
+        bool active = false, exhausted = false;
+        uint32_t p = 0, cur = 0, best = 0, boff = 0, depth = 0, first = 0, room = 0, src4 = 0, tb = 0, nl = 0;
+        bool can4 = false;
+        for (;;) {
+            if (next >= range_end && !exhausted) {  // uniform: take the next chunk
+                uint32_t c = 0;
+                if (lane == 0) c = atomicAdd(&sm.c_search_next, 32u);
+                c = __shfl_sync(BDF_FULL_MASK, c, 0);
+                next = c < nsearch ? c : nsearch;
+                range_end = c + 32u < nsearch ? c + 32u : nsearch;
+                exhausted = c + 32u >= nsearch;
+            }
+            const unsigned idle = __ballot_sync(BDF_FULL_MASK, !active);
+            if (idle && next < range_end) {
+                if (!active) {
+                    const uint32_t q = next + __popc(idle & lanemask_lt());
+                    if (q < range_end) {
+                        p = entry + q;
+                        first = sm.link[p];
+                        if (LISTS) {
+#pragma unroll
+                            for (uint32_t k = 0; k < HCS_NLIST; k += 4)
+                                *reinterpret_cast<uint4 *>(lists + (size_t)p * HCS_NLIST + k) = make_uint4(0, 0, 0, 0);
+                            nl = 0;
+                        }
+                        if (p + 3 > len || first == 0) sm.w.res[q] = 0;
+                        else {
+                            cur = p - first; best = 0; boff = 0; depth = 0;
+                            src4 = hcs_ld32(sm.in, p);
+                            room = len - p < 258u ? len - p : 258u;
+                            can4 = p + 4 <= len;
+                            active = true;
+                        }
+                    }
+                }
+                next += __popc(idle);
+            }
+            if (!__any_sync(BDF_FULL_MASK, active)) {
+                if (next >= range_end && exhausted) break;
+                continue;
+            }
+            if (active) {
+                // a burst of candidates of find_match_impl (src/compress/matchfinder.rs:812-887); most of
+                // them fall at the quick reject (the byte at best_len), which is all the loop carries
+                bool done = false;
+#pragma unroll 1
+                for (int burst = 0; burst < HCS_BURST; burst++) {
+                    const uint32_t off = p - cur;
+                    if (off > 32768u) { done = true; break; }
+                    if (!(best >= 3 && sm.in[cur + best] != tb)) {
+                        const uint32_t m4 = hcs_ld32(sm.in, cur);
+                        const bool eq3 = ((m4 ^ src4) & 0xFFFFFFu) == 0;
+                        if (can4) {
+                            if (m4 == src4) {
+                                const uint32_t l = 4 + hcs_prefix(sm.in, cur + 4, p + 4, room - 4);
+                                if (l > best) {
+                                    best = l; boff = off;
+                                    if (LISTS) { lists[(size_t)p * HCS_NLIST + (nl < HCS_NLIST ? nl : HCS_NLIST - 1)] = l | off << 16; nl++; }
+                                    // nice_len / 258 reached, or nothing longer can follow (the reference
+                                    // leaves its loop at the next candidate: pos + best_len >= len)
+                                    if (l >= prm.nice_len || l == 258 || p + l >= len) { done = true; break; }
+                                    tb = sm.in[p + l];
+                                }
+                            } else if (best < 3 && eq3) {
+                                best = 3; boff = off;
+                                if (LISTS) { lists[(size_t)p * HCS_NLIST] = 3u | off << 16; nl = 1; }
+                                if (p + 3 >= len) { done = true; break; }
+                                tb = sm.in[p + 3];
+                            }
+                        } else if (eq3 && best < 3) {          // room == 3: p + 3 == len
+                            best = 3; boff = off;
+                            if (LISTS) { lists[(size_t)p * HCS_NLIST] = 3u | off << 16; nl = 1; }
+                            done = true;
+                            break;
+                        }
+                    }
+                    // prev_tab is indexed modulo 32768 in the reference: a candidate exactly one
+                    // window back reads the slot the current position has just overwritten
+                    const uint32_t lk = off == 32768u ? first : (uint32_t)sm.link[cur];
+                    if (!lk || lk > cur) { done = true; break; }      // end of the chain (the aliased link can point in front of the stream)
+                    cur -= lk;
+                    if (++depth >= prm.max_depth) { done = true; break; }
+                }
+                if (done) { sm.w.res[p - entry] = best | boff << 16; active = false; }
+            }
+        }
+    }
+}
+
+// the step from every position of the window (decide_greedy_sequences, src/compress/mod.rs:1290-1340)
+__device__ __forceinline__ void hcs_steps_greedy(HcsSmem &sm, uint32_t len, const HcParams &prm, uint32_t entry, uint32_t wvalid)
+{
+    const unsigned tid = threadIdx.x;
+        for (uint32_t i = tid; i < wvalid; i += HCS_THREADS) {
+        const uint32_t p = entry + i;
+        const uint32_t l = sm.w.res[i] & 0xFFFFu;
+        uint32_t v;
+        if (l < 3) v = 1u;
+        else {
+            uint32_t nl = 0, L = l;
+            if (prm.lazy >= 1 && p + 1 < len && l < prm.nice_len) {
+                const uint32_t l1 = sm.w.res[i + 1] & 0xFFFFu;
+                if (l1 > l) {
+                    nl = 1; L = l1;
+                    if (prm.lazy >= 2 && p + 2 < len) {
+                        const uint32_t l2 = sm.w.res[i + 2] & 0xFFFFu;
+                        if (l2 > l1) { nl = 2; L = l2; }
+                    }
+                }
+            }
+            v = (nl + L) | nl << 9 | 1u << 11;
+        }
+        sm.w.nxt[i] = (uint16_t)v;
+    }
+}
+
+// The parse of one window whose steps are in sm.w.nxt (and whose matches are in sm.w.res): path,
+// records, symbol counts; with check_split the place where BlockSplitStats acts and its verdict.
+// Results: sm.c_next_entry (window-relative), sm.c_win_rec, sm.c_pc, sm.c_rec_at_pc, sm.c_split;
+// freq_a / obs_a / cnt_a have been added to the block, freq_b / obs_b / cnt_b are left to the caller.
+__device__ __forceinline__ void hcs_parse_window(HcsSmem &sm, uint32_t len, uint32_t entry, uint32_t wvalid, uint32_t block_start,
+                                                 uint32_t nrec, uint32_t *recs, bool check_split)
+{
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid < HCS_NSEG + 8) sm.seg_entry[tid] = (uint16_t)HCS_NONE;
+    if (tid < HCS_NGRP + 1) sm.grp_entry[tid] = (uint16_t)HCS_NONE;
+    for (uint32_t i = tid; i < 320; i += HCS_THREADS) { sm.freq_a[i] = 0; sm.freq_b[i] = 0; }
+    if (tid < 14) { sm.obs_a[tid] = 0; sm.obs_b[tid] = 0; }
+    if (tid == 0) { sm.cnt_a = 0; sm.cnt_b = 0; sm.c_pc = 0xFFFFFFFFu; sm.c_rec_at_pc = 0; sm.c_split = 0; sm.c_search_next = 0; }
+    __syncthreads();
+    // ---- P2: one thread per segment, backwards: exit and number of steps from every entry
+    if (tid < HCS_NSEG) {
+        const uint32_t s0 = tid * HCS_SEG, s1 = s0 + HCS_SEG;
+        const uint32_t top = s1 < wvalid ? s1 : wvalid;
+        for (uint32_t i = top; i-- > s0; ) {
+            const uint32_t j = i + (sm.w.nxt[i] & 511u);
+            uint32_t ex = j >= s1 ? j - s1 : 0u, st = 1u;       // (0: the stream ends inside this segment)
+            if (j < top) {
+                const uint32_t t = sm.w.sw[j];
+                ex = t & 511u; st += t >> 9;
+            }
+            sm.w.sw[i] = ex | st << 9;
+        }
+    }
+    __syncthreads();
+    // ---- P2b: one warp per group of eight segments, last segment first: exit from the group
+    if (warp < HCS_NGRP) {
+        const uint32_t g0 = warp * HCS_GLEN, g1 = g0 + HCS_GLEN;
+        for (uint32_t s = HCS_GSEG; s-- > 0; ) {
+            const uint32_t i = g0 + s * HCS_SEG + lane, s1 = g0 + (s + 1) * HCS_SEG;
+            if (lane < HCS_SEG && i < wvalid) {
+                const uint32_t x = s1 + (sm.w.sw[i] & 511u);
+                sm.w.ex2[i] = (uint16_t)((x >= g1 || x >= wvalid) ? x : (uint32_t)sm.w.ex2[x]);
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // ---- P3: one thread walks the groups
+    if (tid == 0) {
+        uint32_t cur = 0;
+        while (cur < wvalid) {
+            sm.grp_entry[cur / HCS_GLEN] = (uint16_t)cur;
+            cur = sm.w.ex2[cur];
+        }
+        sm.c_next_entry = cur;
+    }
+    __syncthreads();
+    // ---- one thread per group walks its segments
+    if (tid < HCS_NGRP) {
+        uint32_t cur = sm.grp_entry[tid];
+        const uint32_t g1 = (tid + 1) * HCS_GLEN;
+        if (cur != HCS_NONE) {
+            while (cur < g1 && cur < wvalid) {
+                const uint32_t s = cur / HCS_SEG;
+                sm.seg_entry[s] = (uint16_t)cur;
+                cur = (s + 1) * HCS_SEG + (sm.w.sw[cur] & 511u);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- exclusive scan of the step counts over the entered segments (128 threads)
+    if (tid < 128) {
+        const uint32_t e = tid < HCS_NSEG ? (uint32_t)sm.seg_entry[tid] : HCS_NONE;
+        const uint32_t st = e != HCS_NONE ? sm.w.sw[e] >> 9 : 0u;
+        uint32_t ist = st;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t x = __shfl_up_sync(BDF_FULL_MASK, ist, d);
+            if (lane >= (unsigned)d) ist += x;
+        }
+        if (lane == 31) sm.scan_tmp[warp] = ist;
+        // (warps 0..3 only; a named barrier keeps the other 28 warps out of it)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint32_t base = 0;
+        for (unsigned k = 0; k < warp; k++) base += sm.scan_tmp[k];
+        if (tid < HCS_NSEG) sm.seg_rec[tid] = base + ist - st;
+        if (tid == 127) sm.c_win_obs = base + ist;           // steps of this window
+    }
+    __syncthreads();
+    // ---- every entered segment lists its steps (ex2 is free now); all that follows is per step
+    uint16_t *steps = sm.w.ex2;
+    if (tid < HCS_NSEG) {
+        uint32_t cur = sm.seg_entry[tid];
+        if (cur != HCS_NONE) {
+            uint32_t k = sm.seg_rec[tid];
+            const uint32_t s1 = (tid + 1) * HCS_SEG;
+            while (cur < s1 && cur < wvalid) {
+                steps[k++] = (uint16_t)cur;
+                cur += sm.w.nxt[cur] & 511u;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- records and observations in front of every step: thread t has steps 2t and 2t + 1
+    const uint32_t nsteps = sm.c_win_obs;
+    uint32_t cur0 = 0, cur1 = 0, n0 = 0, n1 = 0, rc0 = 0, rc1 = 0, ob0 = 0, ob1 = 0;
+    if (2 * tid < nsteps) {
+        cur0 = steps[2 * tid]; n0 = sm.w.nxt[cur0];
+        rc0 = ((n0 >> 9) & 3u) + 1u; ob0 = rc0 + ((n0 >> 11) & 1u);
+    }
+    if (2 * tid + 1 < nsteps) {
+        cur1 = steps[2 * tid + 1]; n1 = sm.w.nxt[cur1];
+        rc1 = ((n1 >> 9) & 3u) + 1u; ob1 = rc1 + ((n1 >> 11) & 1u);
+    }
+    uint32_t base_rc, base_ob;
+    {
+        const uint32_t mine = (rc0 + rc1) | (ob0 + ob1) << 16;       // < 65536 each
+        uint32_t inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t x = __shfl_up_sync(BDF_FULL_MASK, inc, d);
+            if (lane >= (unsigned)d) inc += x;
+        }
+        if (lane == 31) sm.seg_obs[warp] = inc;                      // (seg_obs doubles as the scratch of this scan)
+        __syncthreads();
+        uint32_t v = sm.seg_obs[lane], pre = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t x = __shfl_up_sync(BDF_FULL_MASK, pre, d);
+            if (lane >= (unsigned)d) pre += x;
+        }
+        const uint32_t tot = __shfl_sync(BDF_FULL_MASK, pre, 31);
+        const uint32_t wbase = __shfl_sync(BDF_FULL_MASK, pre - v, warp);
+        const uint32_t ex = wbase + inc - mine;
+        base_rc = ex & 0xFFFFu; base_ob = ex >> 16;
+        if (tid == 0) sm.c_win_rec = tot & 0xFFFFu;
+    }
+    // ---- where BlockSplitStats acts (src/compress/mod.rs:387-415): the first step whose top sees
+    // >= 2048 pending observations, a block of >= 5000 bytes and > 5000 bytes left
+    {
+        const uint32_t num_new0 = sm.num_new;
+        if (check_split && 2 * tid < nsteps) {
+            const uint32_t p = entry + cur0;
+            if (num_new0 + base_ob >= 2048u && p - block_start >= 5000u && len - p > 5000u) atomicMin(&sm.c_pc, cur0);
+        }
+        if (check_split && 2 * tid + 1 < nsteps) {
+            const uint32_t p = entry + cur1;
+            if (num_new0 + base_ob + ob0 >= 2048u && p - block_start >= 5000u && len - p > 5000u) atomicMin(&sm.c_pc, cur1);
+        }
+    }
+    __syncthreads();
+    // ---- every step writes its records and counts its symbols
+    const uint32_t pc = sm.c_pc;             // window-relative, 0xFFFFFFFF = no check in this window
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        if (2 * tid + h < nsteps) {
+            const uint32_t cur = h ? cur1 : cur0, n = h ? n1 : n0;
+            uint32_t r = nrec + base_rc + (h ? rc0 : 0u);
+            const bool behind = cur >= pc;
+            if (cur == pc) sm.c_rec_at_pc = r;
+            uint32_t *fq = behind ? sm.freq_b : sm.freq_a;
+            uint32_t *ob = behind ? sm.obs_b : sm.obs_a;
+            const uint32_t nl = (n >> 9) & 3u;
+            const uint32_t p = entry + cur;
+            if (n & 0x800u) {
+                for (uint32_t k = 0; k < nl; k++) {
+                    const uint32_t b = sm.in[p + k];
+                    recs[r++] = b;
+                    atomicAdd(&fq[b], 1u);
+                    atomicAdd(&ob[b >> 5], 1u);
+                }
+                const uint32_t m = sm.w.res[cur + nl], L = m & 0xFFFFu, O = m >> 16;
+                recs[r] = HCS_REC_MATCH | L << 16 | (O - 1u);
+                const unsigned slot = offset_slot_of(O);
+                atomicAdd(&fq[257 + length_slot_of(L)], 1u);
+                atomicAdd(&fq[288 + slot], 1u);
+                atomicAdd(&ob[8 + (L >= 8)], 1u);
+                atomicAdd(&ob[10 + (slot < 16 ? 0 : slot < 24 ? 1 : slot < 30 ? 2 : 0)], 1u);
+                atomicAdd(behind ? &sm.cnt_b : &sm.cnt_a, nl + 2u);
+            } else {
+                const uint32_t b = sm.in[p];
+                recs[r] = b;
+                atomicAdd(&fq[b], 1u);
+                atomicAdd(&ob[b >> 5], 1u);
+                atomicAdd(behind ? &sm.cnt_b : &sm.cnt_a, 1u);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- bookkeeping: what is in front of the check joins the block; the check; the rest
+    for (uint32_t i = tid; i < 320; i += HCS_THREADS) {
+        if (i < 288) sm.litlen_freq[i] += sm.freq_a[i];
+        else sm.offset_freq[i - 288] += sm.freq_a[i];
+    }
+    if (tid < 14) sm.new_obs[tid] += sm.obs_a[tid];
+    __syncthreads();
+    if (tid == 0) {
+        sm.num_new += sm.cnt_a;
+        if (check_split && pc != 0xFFFFFFFFu) sm.c_split = hc_should_end(sm, entry + pc - block_start, len - (entry + pc)) ? 1u : 0u;
+    }
+    __syncthreads();
+}
+
+// One block: the two Huffman codes from the block's histograms, the dynamic header
+// (write_dynamic_huffman_header_impl, src/compress/mod.rs:1775-1883) and the symbols recs[rec_begin, rec_end).
+template <bool SIZE>
+__device__ __forceinline__ void hcs_encode_block(HcsSmem &sm, CtaSink<SIZE> &sink, const uint32_t *recs, uint32_t blk_rec_begin,
+                                                 uint32_t blk_rec_end, bool is_final)
+{
+    const unsigned tid = threadIdx.x;
+    __syncthreads();
+    unsigned nlit_syms = 0, noff_syms = 0, npre = 0, nitems = 0;
+    if (tid == 0) sm.litlen_freq[256]++;
+    __syncthreads();
+    make_huffman_code_cta(288, 14, sm.litlen_freq, sm.litlen_len, sm.enc.litlen_code, sm.enc.scratch);
+    make_huffman_code_cta(32, 15, sm.offset_freq, sm.offset_len, sm.enc.offset_code, sm.enc.scratch);
+    if (tid == 0) {
+        HcsHeaderView hv{sm.litlen_len, sm.offset_len, sm.enc.hdr_lens, sm.enc.hdr_items, sm.enc.pre_freq,
+                         sm.enc.pre_code, sm.enc.pre_len, sm.enc.scratch};
+        hc_prepare_header(hv, nlit_syms, noff_syms, npre, nitems);
+        sm.scan_tmp[0] = nlit_syms; sm.scan_tmp[1] = noff_syms; sm.scan_tmp[2] = npre; sm.scan_tmp[3] = nitems;
+    }
+    sink.begin_block(sm);          // zeroes the staging words (and is the barrier behind thread 0's work)
+    nlit_syms = sm.scan_tmp[0]; noff_syms = sm.scan_tmp[1]; npre = sm.scan_tmp[2]; nitems = sm.scan_tmp[3];
+    {
+        // BFINAL, BTYPE = 2, HLIT, HDIST, HCLEN (thread 0), then the precode lengths (threads 1..19)
+        unsigned long long bits = 0;
+        uint32_t nb = 0;
+        if (tid == 0) {
+            bits = (is_final ? 1u : 0u) | (2u << 1) | ((nlit_syms - 257) << 3) | ((noff_syms - 1) << 8) | ((npre - 4) << 13);
+            nb = 17;
+        } else if (tid <= npre) {
+            const uint8_t perm[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+            bits = sm.enc.pre_len[perm[tid - 1]];
+            nb = 3;
+        }
+        sink.put(sm, bits, nb);
+    }
+    for (uint32_t base = 0; base < nitems; base += HCS_THREADS) {
+        unsigned long long bits = 0;
+        uint32_t nb = 0;
+        if (base + tid < nitems) {
+            const unsigned it = sm.enc.hdr_items[base + tid], sym = it >> 8, extra = it & 0xFF;
+            const unsigned cl = sm.enc.pre_len[sym];
+            bits = sm.enc.pre_code[sym] | (extra << cl);
+            nb = cl + (sym == 16 ? 2 : sym == 17 ? 3 : sym == 18 ? 7 : 0);
+        }
+        sink.put(sm, bits, nb);
+    }
+    for (uint32_t base = blk_rec_begin; base < blk_rec_end; base += HCS_THREADS) {
+        unsigned long long bits = 0;
+        uint32_t nb = 0;
+        if (base + tid < blk_rec_end) {
+            const uint32_t rec = recs[base + tid];
+            if (!(rec & HCS_REC_MATCH)) {
+                bits = sm.enc.litlen_code[rec]; nb = sm.litlen_len[rec];
+            } else {
+                const uint32_t L = (rec >> 16) & 0x1FFu, O = (rec & 0x7FFFu) + 1u;
+                unsigned lslot = length_slot_of(L), lb, le;
+                length_slot_info(lslot, lb, le);
+                const unsigned lcl = sm.litlen_len[257 + lslot];
+                const uint32_t lbits = sm.enc.litlen_code[257 + lslot] | ((L - lb) << lcl);
+                const uint32_t lnb = lcl + le;
+                unsigned oslot = offset_slot_of(O), ob_, oe;
+                offset_slot_info(oslot, ob_, oe);
+                const unsigned ocl = sm.offset_len[oslot];
+                const uint32_t obits = sm.enc.offset_code[oslot] | ((O - ob_) << ocl);
+                bits = (unsigned long long)obits << lnb | lbits;
+                nb = lnb + ocl + oe;
+            }
+        }
+        sink.put(sm, bits, nb);
+    }
+    sink.put(sm, tid == 0 ? sm.enc.litlen_code[256] : 0u, tid == 0 ? sm.litlen_len[256] : 0u);
+}
+
+// The end of a stream: sync flush / padding, footer, results (warp 0).
+template <bool SIZE>
+__device__ __forceinline__ void hcs_finish_stream(HcsSmem &sm, const DeflateArgs &a, unsigned long long idx, const uint8_t *gin,
+                                                  uint32_t len, uint8_t *out, unsigned hdr, unsigned uflags)
+{
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    __syncthreads();
+    if (warp == 0) {
+        // FlushMode::Sync (:662-681): 3 zero bits, pad to a byte, 00 00 FF FF; otherwise pad to a byte
+        unsigned long long sz = sm.sink_flushed;
+        uint32_t pend = sm.sink_bits;
+        bool over = sm.sink_overflow != 0;
+        const unsigned long long cap = SIZE ? ~0ull : unit_cap(len, uflags);
+        uint32_t tail_bytes = 0;
+        uint8_t tail[6];
+        uint32_t carry = SIZE ? 0u : (sm.sink_carry & 0xFFu);
+        if (uflags & UNIT_SYNC) {
+            pend += 3;
+            if (pend > 8) { tail[tail_bytes++] = (uint8_t)carry; carry = 0; pend -= 8; }
+            tail[tail_bytes++] = (uint8_t)carry;          // padded to the byte
+            tail[tail_bytes++] = 0; tail[tail_bytes++] = 0; tail[tail_bytes++] = 0xFF; tail[tail_bytes++] = 0xFF;
+        } else if (pend) {
+            tail[tail_bytes++] = (uint8_t)carry;
+        }
+        if (sz + tail_bytes > cap) over = true;
+        if (!SIZE && !over && lane < tail_bytes) out[hdr + sz + lane] = tail[lane];
+        sz += tail_bytes;
+        int st = BDF_OK;
+        if (over) { st = BDF_INSUFFICIENT_SPACE; sz = 0; }
+        else if (!SIZE) sz = frame_footer(a.format, gin, len, out, hdr + sz, g_crc_tables.slice, g_crc_tables.x2n, lane);
+        if (lane == 0) { a.status[idx] = st; a.out_size[idx] = sz; }
+    }
+}
+
 template <bool SIZE>
 __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_hcs_kernel(DeflateArgs a)
 {
@@ -252,97 +814,10 @@ __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_hcs_kernel(DeflateArgs
             continue;
         }
         const uint32_t len = (uint32_t)len64;
-        const uint32_t gmis = (uint32_t)(reinterpret_cast<uintptr_t>(gin) & 3u);
-        const uint32_t *gw = reinterpret_cast<const uint32_t *>(gin - gmis);     // aligned words that hold the stream
-        // 4 bytes of the stream at p (only words that hold a byte of the stream are touched)
-        auto g32 = [&](uint32_t p) -> uint32_t {
-            const uint32_t q = p + gmis, k = q >> 2, sh = 8u * (q & 3u);
-            const uint32_t w0 = __ldg(gw + k);
-            if (sh == 0) return w0;
-            const uint32_t w1 = (k + 1) * 4u < len + gmis ? __ldg(gw + k + 1) : 0u;
-            return __funnelshift_r(w0, w1, sh);
-        };
-
-        // ================================================= phase 1: chains of the whole stream
-        for (uint32_t i = tid; i < 32768 / 8; i += HCS_THREADS) reinterpret_cast<uint4 *>(sm.head)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
-        for (uint32_t i = tid; i < 65536 / 8; i += HCS_THREADS) reinterpret_cast<uint4 *>(sm.link)[i] = make_uint4(0, 0, 0, 0);
-        uint32_t l_head = 0, l_tail = 0;       // inserting warps: ring indices into their list (uniform per warp)
-        for (uint32_t b0 = 0; b0 < len; b0 += HCS_IBLK) {
-            __syncthreads();
-            for (uint32_t k = tid; k < HCS_INS_WARPS * (HCS_IBLK / 32); k += HCS_THREADS) (&sm.ins.cls[0][0])[k] = 0;
-            __syncthreads();
-            // (i) hash of every position of the round, and one bit in the row of the warp that will link
-            // it; the last two positions of a stream are never inserted
-            for (uint32_t k = tid; k < HCS_IBLK; k += HCS_THREADS) {
-                const uint32_t p = b0 + k;
-                if (p + 3 <= len) {
-                    const uint32_t h = hash3(g32(p) & 0xFFFFFFu);
-                    sm.ins.hbuf[k] = (uint16_t)h;
-                    atomicOr(&sm.ins.cls[h & (HCS_INS_WARPS - 1)][k >> 5], 1u << (k & 31u));
-                }
-            }
-            __syncthreads();
-            // (ii) warp w links the positions whose hash is w modulo 16, in ascending order: it
-            // collects them from its bit row (8 positions per lane and step) and links 32 at a time.
-            // Chains of different hash values never touch, so the warps do not wait for one another.
-            if (warp < HCS_INS_WARPS) {
-                uint16_t *list = sm.ins.list[warp];
-                const uint32_t nblk = len - b0 < HCS_IBLK ? len - b0 : HCS_IBLK;
-                auto link_some = [&](uint32_t have) {
-                    const bool ok = lane < have;
-                    uint32_t k = 0, h = 0x10000u + lane;          // unique key for idle lanes
-                    if (ok) { k = list[(l_head + lane) % HCS_LIST]; h = sm.ins.hbuf[k]; }
-                    const uint32_t p = b0 + k;
-                    const unsigned peers = __match_any_sync(BDF_FULL_MASK, h);
-                    const unsigned lower = peers & lanemask_lt();
-                    const uint32_t peer_pos = __shfl_sync(BDF_FULL_MASK, p, lower ? 31 - __clz(lower) : 0);
-                    if (ok) {
-                        const uint32_t prev = lower ? peer_pos : (uint32_t)sm.head[h];
-                        sm.link[p] = (!lower && prev == HCS_NONE) ? (uint16_t)0 : (uint16_t)(p - prev);
-                    }
-                    __syncwarp();
-                    if (ok && (peers >> lane) == 1u) sm.head[h] = (uint16_t)p;
-                    __syncwarp();
-                    l_head += have;
-                };
-                for (uint32_t s0 = 0; s0 < nblk; s0 += 256) {
-                    uint32_t mine = (sm.ins.cls[warp][(s0 >> 5) + (lane >> 2)] >> (8u * (lane & 3u))) & 0xFFu;
-                    const uint32_t cnt = __popc(mine);
-                    uint32_t incl = cnt;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t t = __shfl_up_sync(BDF_FULL_MASK, incl, d);
-                        if (lane >= (unsigned)d) incl += t;
-                    }
-                    uint32_t at = l_tail + incl - cnt;
-                    while (mine) {
-                        const uint32_t k = __ffs(mine) - 1;
-                        mine &= mine - 1;
-                        list[at % HCS_LIST] = (uint16_t)(s0 + 8 * lane + k);    // position inside the round
-                        at++;
-                    }
-                    l_tail += __shfl_sync(BDF_FULL_MASK, incl, 31);
-                    __syncwarp();
-                    while (l_tail - l_head >= 32u) link_some(32u);
-                }
-                while (l_tail != l_head) link_some(l_tail - l_head < 32u ? l_tail - l_head : 32u);   // the buffer is rewritten next round
-            }
-        }
-        __syncthreads();
-
-        // ================================================= phase 2: the stream moves into shared memory
-        {
-            uint32_t *iw = reinterpret_cast<uint32_t *>(sm.in);
-            const uint32_t nw = (len + 3) >> 2;
-            for (uint32_t k = tid; k < (65536 + 32) / 4; k += HCS_THREADS) {
-                uint32_t v = 0;
-                if (k < nw) {
-                    v = g32(4 * k);
-                    if (4 * k + 4 > len) v &= 0xFFFFFFFFu >> (8 * (4 * k + 4 - len));     // zero padding behind the stream
-                }
-                iw[k] = v;
-            }
-        }
+        HcsStream st;
+        st.set(gin, len);
+        hcs_build_chains(sm, st);
+        hcs_stage_input(sm, st);
         CtaSink<SIZE> sink;
         if (warp == 0 && !SIZE) frame_header(a.format, a.level, out, lane);
         const unsigned hdr = SIZE ? 0u : a.format == BDF_ZLIB ? 2u : a.format == BDF_GZIP ? 10u : 0u;   // what frame_header wrote
@@ -362,299 +837,11 @@ __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_hcs_kernel(DeflateArgs
         while (more) {
             const uint32_t wvalid = len - entry < HCS_W ? len - entry : HCS_W;      // positions parsed in this window
             const uint32_t nsearch = len - entry < HCS_SEARCH ? len - entry : HCS_SEARCH;
-            // ---- search: warps take chunks of 32 positions from a counter; every lane walks one chain at a
-            // time and takes the next position of the chunk as soon as it is done
-            {
-                uint32_t next = 0, range_end = 0;
-                bool active = false, exhausted = false;
-                uint32_t p = 0, cur = 0, best = 0, boff = 0, depth = 0, first = 0, room = 0, src4 = 0, tb = 0;
-                bool can4 = false;
-                for (;;) {
-                    if (next >= range_end && !exhausted) {  // uniform: take the next chunk
-                        uint32_t c = 0;
-                        if (lane == 0) c = atomicAdd(&sm.c_search_next, 32u);
-                        c = __shfl_sync(BDF_FULL_MASK, c, 0);
-                        next = c < nsearch ? c : nsearch;
-                        range_end = c + 32u < nsearch ? c + 32u : nsearch;
-                        exhausted = c + 32u >= nsearch;
-                    }
-                    const unsigned idle = __ballot_sync(BDF_FULL_MASK, !active);
-                    if (idle && next < range_end) {
-                        if (!active) {
-                            const uint32_t q = next + __popc(idle & lanemask_lt());
-                            if (q < range_end) {
-                                p = entry + q;
-                                first = sm.link[p];
-                                if (p + 3 > len || first == 0) sm.w.res[q] = 0;
-                                else {
-                                    cur = p - first; best = 0; boff = 0; depth = 0;
-                                    src4 = hcs_ld32(sm.in, p);
-                                    room = len - p < 258u ? len - p : 258u;
-                                    can4 = p + 4 <= len;
-                                    active = true;
-                                }
-                            }
-                        }
-                        next += __popc(idle);
-                    }
-                    if (!__any_sync(BDF_FULL_MASK, active)) {
-                        if (next >= range_end && exhausted) break;
-                        continue;
-                    }
-                    if (active) {
-                        // a burst of candidates of find_match_impl (src/compress/matchfinder.rs:812-887); most of
-                        // them fall at the quick reject (the byte at best_len), which is all the loop carries
-                        bool done = false;
-#pragma unroll 1
-                        for (int burst = 0; burst < HCS_BURST; burst++) {
-                            const uint32_t off = p - cur;
-                            if (off > 32768u) { done = true; break; }
-                            if (!(best >= 3 && sm.in[cur + best] != tb)) {
-                                const uint32_t m4 = hcs_ld32(sm.in, cur);
-                                const bool eq3 = ((m4 ^ src4) & 0xFFFFFFu) == 0;
-                                if (can4) {
-                                    if (m4 == src4) {
-                                        const uint32_t l = 4 + hcs_prefix(sm.in, cur + 4, p + 4, room - 4);
-                                        if (l > best) {
-                                            best = l; boff = off;
-                                            // nice_len / 258 reached, or nothing longer can follow (the reference
-                                            // leaves its loop at the next candidate: pos + best_len >= len)
-                                            if (l >= prm.nice_len || l == 258 || p + l >= len) { done = true; break; }
-                                            tb = sm.in[p + l];
-                                        }
-                                    } else if (best < 3 && eq3) {
-                                        best = 3; boff = off;
-                                        if (p + 3 >= len) { done = true; break; }
-                                        tb = sm.in[p + 3];
-                                    }
-                                } else if (eq3 && best < 3) {          // room == 3: p + 3 == len
-                                    best = 3; boff = off;
-                                    done = true;
-                                    break;
-                                }
-                            }
-                            // prev_tab is indexed modulo 32768 in the reference: a candidate exactly one
-                            // window back reads the slot the current position has just overwritten
-                            const uint32_t lk = off == 32768u ? first : (uint32_t)sm.link[cur];
-                            if (!lk || lk > cur) { done = true; break; }      // end of the chain (the aliased link can point in front of the stream)
-                            cur -= lk;
-                            if (++depth >= prm.max_depth) { done = true; break; }
-                        }
-                        if (done) { sm.w.res[p - entry] = best | boff << 16; active = false; }
-                    }
-                }
-            }
+            hcs_search<false>(sm, len, prm, entry, nsearch, nullptr);
             __syncthreads();
-            // ---- P1: the step from every position (decide_greedy_sequences, src/compress/mod.rs:1290-1340)
-            for (uint32_t i = tid; i < wvalid; i += HCS_THREADS) {
-                const uint32_t p = entry + i;
-                const uint32_t l = sm.w.res[i] & 0xFFFFu;
-                uint32_t v;
-                if (l < 3) v = 1u;
-                else {
-                    uint32_t nl = 0, L = l;
-                    if (prm.lazy >= 1 && p + 1 < len && l < prm.nice_len) {
-                        const uint32_t l1 = sm.w.res[i + 1] & 0xFFFFu;
-                        if (l1 > l) {
-                            nl = 1; L = l1;
-                            if (prm.lazy >= 2 && p + 2 < len) {
-                                const uint32_t l2 = sm.w.res[i + 2] & 0xFFFFu;
-                                if (l2 > l1) { nl = 2; L = l2; }
-                            }
-                        }
-                    }
-                    v = (nl + L) | nl << 9 | 1u << 11;
-                }
-                sm.w.nxt[i] = (uint16_t)v;
-            }
-            if (tid < HCS_NSEG + 8) sm.seg_entry[tid] = (uint16_t)HCS_NONE;
-            if (tid < HCS_NGRP + 1) sm.grp_entry[tid] = (uint16_t)HCS_NONE;
-            for (uint32_t i = tid; i < 320; i += HCS_THREADS) { sm.freq_a[i] = 0; sm.freq_b[i] = 0; }
-            if (tid < 14) { sm.obs_a[tid] = 0; sm.obs_b[tid] = 0; }
-            if (tid == 0) { sm.cnt_a = 0; sm.cnt_b = 0; sm.c_pc = 0xFFFFFFFFu; sm.c_rec_at_pc = 0; sm.c_split = 0; sm.c_search_next = 0; }
-            __syncthreads();
-            // ---- P2: one thread per segment, backwards: exit and number of steps from every entry
-            if (tid < HCS_NSEG) {
-                const uint32_t s0 = tid * HCS_SEG, s1 = s0 + HCS_SEG;
-                const uint32_t top = s1 < wvalid ? s1 : wvalid;
-                for (uint32_t i = top; i-- > s0; ) {
-                    const uint32_t j = i + (sm.w.nxt[i] & 511u);
-                    uint32_t ex = j >= s1 ? j - s1 : 0u, st = 1u;       // (0: the stream ends inside this segment)
-                    if (j < top) {
-                        const uint32_t t = sm.w.sw[j];
-                        ex = t & 511u; st += t >> 9;
-                    }
-                    sm.w.sw[i] = ex | st << 9;
-                }
-            }
-            __syncthreads();
-            // ---- P2b: one warp per group of eight segments, last segment first: exit from the group
-            if (warp < HCS_NGRP) {
-                const uint32_t g0 = warp * HCS_GLEN, g1 = g0 + HCS_GLEN;
-                for (uint32_t s = HCS_GSEG; s-- > 0; ) {
-                    const uint32_t i = g0 + s * HCS_SEG + lane, s1 = g0 + (s + 1) * HCS_SEG;
-                    if (lane < HCS_SEG && i < wvalid) {
-                        const uint32_t x = s1 + (sm.w.sw[i] & 511u);
-                        sm.w.ex2[i] = (uint16_t)((x >= g1 || x >= wvalid) ? x : (uint32_t)sm.w.ex2[x]);
-                    }
-                    __syncwarp();
-                }
-            }
-            __syncthreads();
-            // ---- P3: one thread walks the groups
-            if (tid == 0) {
-                uint32_t cur = 0;
-                while (cur < wvalid) {
-                    sm.grp_entry[cur / HCS_GLEN] = (uint16_t)cur;
-                    cur = sm.w.ex2[cur];
-                }
-                sm.c_next_entry = cur;
-            }
-            __syncthreads();
-            // ---- one thread per group walks its segments
-            if (tid < HCS_NGRP) {
-                uint32_t cur = sm.grp_entry[tid];
-                const uint32_t g1 = (tid + 1) * HCS_GLEN;
-                if (cur != HCS_NONE) {
-                    while (cur < g1 && cur < wvalid) {
-                        const uint32_t s = cur / HCS_SEG;
-                        sm.seg_entry[s] = (uint16_t)cur;
-                        cur = (s + 1) * HCS_SEG + (sm.w.sw[cur] & 511u);
-                    }
-                }
-            }
-            __syncthreads();
-            // ---- exclusive scan of the step counts over the entered segments (128 threads)
-            if (tid < 128) {
-                const uint32_t e = tid < HCS_NSEG ? (uint32_t)sm.seg_entry[tid] : HCS_NONE;
-                const uint32_t st = e != HCS_NONE ? sm.w.sw[e] >> 9 : 0u;
-                uint32_t ist = st;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t x = __shfl_up_sync(BDF_FULL_MASK, ist, d);
-                    if (lane >= (unsigned)d) ist += x;
-                }
-                if (lane == 31) sm.scan_tmp[warp] = ist;
-                // (warps 0..3 only; a named barrier keeps the other 28 warps out of it)
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                uint32_t base = 0;
-                for (unsigned k = 0; k < warp; k++) base += sm.scan_tmp[k];
-                if (tid < HCS_NSEG) sm.seg_rec[tid] = base + ist - st;
-                if (tid == 127) sm.c_win_obs = base + ist;           // steps of this window
-            }
-            __syncthreads();
-            // ---- every entered segment lists its steps (ex2 is free now); all that follows is per step
-            uint16_t *steps = sm.w.ex2;
-            if (tid < HCS_NSEG) {
-                uint32_t cur = sm.seg_entry[tid];
-                if (cur != HCS_NONE) {
-                    uint32_t k = sm.seg_rec[tid];
-                    const uint32_t s1 = (tid + 1) * HCS_SEG;
-                    while (cur < s1 && cur < wvalid) {
-                        steps[k++] = (uint16_t)cur;
-                        cur += sm.w.nxt[cur] & 511u;
-                    }
-                }
-            }
-            __syncthreads();
-            // ---- records and observations in front of every step: thread t has steps 2t and 2t + 1
-            const uint32_t nsteps = sm.c_win_obs;
-            uint32_t cur0 = 0, cur1 = 0, n0 = 0, n1 = 0, rc0 = 0, rc1 = 0, ob0 = 0, ob1 = 0;
-            if (2 * tid < nsteps) {
-                cur0 = steps[2 * tid]; n0 = sm.w.nxt[cur0];
-                rc0 = ((n0 >> 9) & 3u) + 1u; ob0 = rc0 + ((n0 >> 11) & 1u);
-            }
-            if (2 * tid + 1 < nsteps) {
-                cur1 = steps[2 * tid + 1]; n1 = sm.w.nxt[cur1];
-                rc1 = ((n1 >> 9) & 3u) + 1u; ob1 = rc1 + ((n1 >> 11) & 1u);
-            }
-            uint32_t base_rc, base_ob;
-            {
-                const uint32_t mine = (rc0 + rc1) | (ob0 + ob1) << 16;       // < 65536 each
-                uint32_t inc = mine;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t x = __shfl_up_sync(BDF_FULL_MASK, inc, d);
-                    if (lane >= (unsigned)d) inc += x;
-                }
-                if (lane == 31) sm.seg_obs[warp] = inc;                      // (seg_obs doubles as the scratch of this scan)
-                __syncthreads();
-                uint32_t v = sm.seg_obs[lane], pre = v;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t x = __shfl_up_sync(BDF_FULL_MASK, pre, d);
-                    if (lane >= (unsigned)d) pre += x;
-                }
-                const uint32_t tot = __shfl_sync(BDF_FULL_MASK, pre, 31);
-                const uint32_t wbase = __shfl_sync(BDF_FULL_MASK, pre - v, warp);
-                const uint32_t ex = wbase + inc - mine;
-                base_rc = ex & 0xFFFFu; base_ob = ex >> 16;
-                if (tid == 0) sm.c_win_rec = tot & 0xFFFFu;
-            }
-            // ---- where BlockSplitStats acts (src/compress/mod.rs:387-415): the first step whose top sees
-            // >= 2048 pending observations, a block of >= 5000 bytes and > 5000 bytes left
-            {
-                const uint32_t num_new0 = sm.num_new;
-                if (2 * tid < nsteps) {
-                    const uint32_t p = entry + cur0;
-                    if (num_new0 + base_ob >= 2048u && p - block_start >= 5000u && len - p > 5000u) atomicMin(&sm.c_pc, cur0);
-                }
-                if (2 * tid + 1 < nsteps) {
-                    const uint32_t p = entry + cur1;
-                    if (num_new0 + base_ob + ob0 >= 2048u && p - block_start >= 5000u && len - p > 5000u) atomicMin(&sm.c_pc, cur1);
-                }
-            }
-            __syncthreads();
-            // ---- every step writes its records and counts its symbols
-            const uint32_t pc = sm.c_pc;             // window-relative, 0xFFFFFFFF = no check in this window
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                if (2 * tid + h < nsteps) {
-                    const uint32_t cur = h ? cur1 : cur0, n = h ? n1 : n0;
-                    uint32_t r = nrec + base_rc + (h ? rc0 : 0u);
-                    const bool behind = cur >= pc;
-                    if (cur == pc) sm.c_rec_at_pc = r;
-                    uint32_t *fq = behind ? sm.freq_b : sm.freq_a;
-                    uint32_t *ob = behind ? sm.obs_b : sm.obs_a;
-                    const uint32_t nl = (n >> 9) & 3u;
-                    const uint32_t p = entry + cur;
-                    if (n & 0x800u) {
-                        for (uint32_t k = 0; k < nl; k++) {
-                            const uint32_t b = sm.in[p + k];
-                            recs[r++] = b;
-                            atomicAdd(&fq[b], 1u);
-                            atomicAdd(&ob[b >> 5], 1u);
-                        }
-                        const uint32_t m = sm.w.res[cur + nl], L = m & 0xFFFFu, O = m >> 16;
-                        recs[r] = HCS_REC_MATCH | L << 16 | (O - 1u);
-                        const unsigned slot = offset_slot_of(O);
-                        atomicAdd(&fq[257 + length_slot_of(L)], 1u);
-                        atomicAdd(&fq[288 + slot], 1u);
-                        atomicAdd(&ob[8 + (L >= 8)], 1u);
-                        atomicAdd(&ob[10 + (slot < 16 ? 0 : slot < 24 ? 1 : slot < 30 ? 2 : 0)], 1u);
-                        atomicAdd(behind ? &sm.cnt_b : &sm.cnt_a, nl + 2u);
-                    } else {
-                        const uint32_t b = sm.in[p];
-                        recs[r] = b;
-                        atomicAdd(&fq[b], 1u);
-                        atomicAdd(&ob[b >> 5], 1u);
-                        atomicAdd(behind ? &sm.cnt_b : &sm.cnt_a, 1u);
-                    }
-                }
-            }
-            __syncthreads();
-            // ---- bookkeeping: what is in front of the check joins the block; the check; the rest
-            for (uint32_t i = tid; i < 320; i += HCS_THREADS) {
-                if (i < 288) sm.litlen_freq[i] += sm.freq_a[i];
-                else sm.offset_freq[i - 288] += sm.freq_a[i];
-            }
-            if (tid < 14) sm.new_obs[tid] += sm.obs_a[tid];
-            __syncthreads();
-            if (tid == 0) {
-                sm.num_new += sm.cnt_a;
-                if (pc != 0xFFFFFFFFu) sm.c_split = hc_should_end(sm, entry + pc - block_start, len - (entry + pc)) ? 1u : 0u;
-            }
-            __syncthreads();
+            hcs_steps_greedy(sm, len, prm, entry, wvalid);
+            hcs_parse_window(sm, len, entry, wvalid, block_start, nrec, recs, true);
+            const uint32_t pc = sm.c_pc;
             const uint32_t win_rec = sm.c_win_rec;
             const uint32_t next_entry = entry + sm.c_next_entry;
             const bool split = sm.c_split != 0;
@@ -678,71 +865,7 @@ __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_hcs_kernel(DeflateArgs
                 }
                 const uint32_t blk_rec_end = do_split ? sm.c_rec_at_pc : nrec + win_rec;
                 const bool is_final = do_last && (uflags & UNIT_FINISH);
-                // ---------------------------------------------- one block: codes, header, symbols
-                __syncthreads();
-                unsigned nlit_syms = 0, noff_syms = 0, npre = 0, nitems = 0;
-                if (tid == 0) sm.litlen_freq[256]++;
-                __syncthreads();
-                make_huffman_code_cta(288, 14, sm.litlen_freq, sm.litlen_len, sm.enc.litlen_code, sm.enc.scratch);
-                make_huffman_code_cta(32, 15, sm.offset_freq, sm.offset_len, sm.enc.offset_code, sm.enc.scratch);
-                if (tid == 0) {
-                    HcsHeaderView hv{sm.litlen_len, sm.offset_len, sm.enc.hdr_lens, sm.enc.hdr_items, sm.enc.pre_freq,
-                                     sm.enc.pre_code, sm.enc.pre_len, sm.enc.scratch};
-                    hc_prepare_header(hv, nlit_syms, noff_syms, npre, nitems);
-                    sm.scan_tmp[0] = nlit_syms; sm.scan_tmp[1] = noff_syms; sm.scan_tmp[2] = npre; sm.scan_tmp[3] = nitems;
-                }
-                sink.begin_block(sm);          // zeroes the staging words (and is the barrier behind thread 0's work)
-                nlit_syms = sm.scan_tmp[0]; noff_syms = sm.scan_tmp[1]; npre = sm.scan_tmp[2]; nitems = sm.scan_tmp[3];
-                {
-                    // BFINAL, BTYPE = 2, HLIT, HDIST, HCLEN (thread 0), then the precode lengths (threads 1..19)
-                    unsigned long long bits = 0;
-                    uint32_t nb = 0;
-                    if (tid == 0) {
-                        bits = (is_final ? 1u : 0u) | (2u << 1) | ((nlit_syms - 257) << 3) | ((noff_syms - 1) << 8) | ((npre - 4) << 13);
-                        nb = 17;
-                    } else if (tid <= npre) {
-                        const uint8_t perm[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-                        bits = sm.enc.pre_len[perm[tid - 1]];
-                        nb = 3;
-                    }
-                    sink.put(sm, bits, nb);
-                }
-                for (uint32_t base = 0; base < nitems; base += HCS_THREADS) {
-                    unsigned long long bits = 0;
-                    uint32_t nb = 0;
-                    if (base + tid < nitems) {
-                        const unsigned it = sm.enc.hdr_items[base + tid], sym = it >> 8, extra = it & 0xFF;
-                        const unsigned cl = sm.enc.pre_len[sym];
-                        bits = sm.enc.pre_code[sym] | (extra << cl);
-                        nb = cl + (sym == 16 ? 2 : sym == 17 ? 3 : sym == 18 ? 7 : 0);
-                    }
-                    sink.put(sm, bits, nb);
-                }
-                for (uint32_t base = blk_rec_begin; base < blk_rec_end; base += HCS_THREADS) {
-                    unsigned long long bits = 0;
-                    uint32_t nb = 0;
-                    if (base + tid < blk_rec_end) {
-                        const uint32_t rec = recs[base + tid];
-                        if (!(rec & HCS_REC_MATCH)) {
-                            bits = sm.enc.litlen_code[rec]; nb = sm.litlen_len[rec];
-                        } else {
-                            const uint32_t L = (rec >> 16) & 0x1FFu, O = (rec & 0x7FFFu) + 1u;
-                            unsigned lslot = length_slot_of(L), lb, le;
-                            length_slot_info(lslot, lb, le);
-                            const unsigned lcl = sm.litlen_len[257 + lslot];
-                            const uint32_t lbits = sm.enc.litlen_code[257 + lslot] | ((L - lb) << lcl);
-                            const uint32_t lnb = lcl + le;
-                            unsigned oslot = offset_slot_of(O), ob_, oe;
-                            offset_slot_info(oslot, ob_, oe);
-                            const unsigned ocl = sm.offset_len[oslot];
-                            const uint32_t obits = sm.enc.offset_code[oslot] | ((O - ob_) << ocl);
-                            bits = (unsigned long long)obits << lnb | lbits;
-                            nb = lnb + ocl + oe;
-                        }
-                    }
-                    sink.put(sm, bits, nb);
-                }
-                sink.put(sm, tid == 0 ? sm.enc.litlen_code[256] : 0u, tid == 0 ? sm.litlen_len[256] : 0u);
+                hcs_encode_block<SIZE>(sm, sink, recs, blk_rec_begin, blk_rec_end, is_final);
                 // ---------------------------------------------- the next block starts empty
                 if (do_split) {
                     block_start = entry + pc;
@@ -762,33 +885,241 @@ __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_hcs_kernel(DeflateArgs
         }
         // an empty input is one block that holds only the end-of-block symbol (src/compress/mod.rs:648-660):
         // the window loop above ran once with nothing to parse and encoded it as the last block
-        // ================================================= the end of the stream
+        hcs_finish_stream<SIZE>(sm, a, idx, gin, len, out, hdr, uflags);
+    }
+}
+
+// ---- levels 10..12 for streams of at most 64 KiB: a near-optimal parser on the same machinery.
+// Replaces compress_near_optimal_block (src/compress/mod.rs:1586-1773) and the binary-tree
+// matchfinder it drives (matchfinder.rs:1234-1776) for the batch path; this tier is held to the
+// reference's SIZE (within 0.5 %), not to its bytes, so the parser is free:
+//   * matches come from the hash chains: one pass over all positions keeps, per position, the best
+//     match (for the greedy pass) and the list of improvements along the chain (len, offset of
+//     strictly increasing length — what find_matches hands the reference's DP);
+//   * pass 1, like the reference's: a greedy parse with BlockSplitStats decides where the block
+//     ends and gives the histograms the symbol costs come from;
+//   * pass 2 is a shortest path over the block like the reference's, but run BACKWARDS (cost to the
+//     end of the block): one warp, three positions per step (a match is at least 3 long, so the
+//     match edges of three neighbours only look at costs that are already final; their literal
+//     edges are then chained), eight list entries per position in parallel lanes.  Running it
+//     backwards makes the result a step function — exactly what the parallel parse of this file
+//     consumes, so there is no serial backtrack;
+//   * pass 3: that parse over the block (records, final histograms), then the block is encoded.
+constexpr size_t NOS_SCRATCH_PER_CTA = HCS_SCRATCH_PER_CTA + 65536 * sizeof(uint32_t) * 2 + 65536 * HCS_NLIST * sizeof(uint32_t);
+constexpr uint32_t NOS_INF = 0x0FFFFFFFu;
+constexpr uint32_t NOS_SHORTER = 7;
+
+__device__ __forceinline__ HcParams nos_params(int level)
+{
+    // depth / nice length of the chain walks.  The reference's binary trees search 35 / 100 / 300 nodes
+    // deep (nice 75 / 150 / 258); a chain of 3-byte hashes has to walk further to see the same matches
+    // (measured on text: depth 70 -> 3.1 % above the reference's size at level 10, 160 -> 1.2 %).
+    HcParams p;
+    if (level <= 10) { p.max_depth = 250; p.nice_len = 75; }
+    else if (level == 11) { p.max_depth = 400; p.nice_len = 150; }
+    else { p.max_depth = 600; p.nice_len = 258; }
+    p.lazy = 0;
+    return p;
+}
+
+__global__ void __launch_bounds__(HCS_THREADS, 1) deflate_nos_kernel(DeflateArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HcsSmem &sm = *reinterpret_cast<HcsSmem *>(smem_raw);
+    __shared__ unsigned long long s_idx;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const HcParams prm = nos_params(a.level);
+    uint8_t *slab = static_cast<uint8_t *>(a.scratch) + a.scratch_stride * blockIdx.x;
+    uint32_t *recs = reinterpret_cast<uint32_t *>(slab);
+    uint32_t *gbest = reinterpret_cast<uint32_t *>(slab + HCS_SCRATCH_PER_CTA);
+    uint32_t *choice = gbest + 65536;
+    uint32_t *lists = choice + 65536;
+
+    for (;;) {
         __syncthreads();
-        if (warp == 0) {
-            // FlushMode::Sync (:662-681): 3 zero bits, pad to a byte, 00 00 FF FF; otherwise pad to a byte
-            unsigned long long sz = sm.sink_flushed;
-            uint32_t pend = sm.sink_bits;
-            bool over = sm.sink_overflow != 0;
-            const unsigned long long cap = SIZE ? ~0ull : unit_cap(len, uflags);
-            uint32_t tail_bytes = 0;
-            uint8_t tail[6];
-            uint32_t carry = SIZE ? 0u : (sm.sink_carry & 0xFFu);
-            if (uflags & UNIT_SYNC) {
-                pend += 3;
-                if (pend > 8) { tail[tail_bytes++] = (uint8_t)carry; carry = 0; pend -= 8; }
-                tail[tail_bytes++] = (uint8_t)carry;          // padded to the byte
-                tail[tail_bytes++] = 0; tail[tail_bytes++] = 0; tail[tail_bytes++] = 0xFF; tail[tail_bytes++] = 0xFF;
-            } else if (pend) {
-                tail[tail_bytes++] = (uint8_t)carry;
-            }
-            if (sz + tail_bytes > cap) over = true;
-            if (!SIZE && !over && lane < tail_bytes) out[hdr + sz + lane] = tail[lane];
-            sz += tail_bytes;
-            int st = BDF_OK;
-            if (over) { st = BDF_INSUFFICIENT_SPACE; sz = 0; }
-            else if (!SIZE) sz = frame_footer(a.format, gin, len, out, hdr + sz, g_crc_tables.slice, g_crc_tables.x2n, lane);
-            if (lane == 0) { a.status[idx] = st; a.out_size[idx] = sz; }
+        if (tid == 0) s_idx = atomicAdd(a.work_counter, 1ull);
+        __syncthreads();
+        const unsigned long long idx = s_idx;
+        if (idx >= a.n) break;
+        const uint8_t *gin = a.in + a.in_off[idx];
+        const uint64_t len64 = a.in_off[idx + 1] - a.in_off[idx];
+        uint8_t *out = a.out + a.out_off[idx];
+        const unsigned uflags = unit_flags_of(a, idx);
+        if (len64 > 65536) {
+            if (tid == 0) { a.status[idx] = BDF_STREAM_UNSUPPORTED; a.out_size[idx] = 0; }
+            continue;
         }
+        const uint32_t len = (uint32_t)len64;
+        HcsStream st;
+        st.set(gin, len);
+        hcs_build_chains(sm, st);
+        hcs_stage_input(sm, st);
+        CtaSink<false> sink;
+        if (warp == 0) frame_header(a.format, a.level, out, lane);
+        const unsigned hdr = a.format == BDF_ZLIB ? 2u : a.format == BDF_GZIP ? 10u : 0u;
+        sink.init(sm, out + hdr, unit_cap(len, uflags));
+        if (tid == 0) sm.c_search_next = 0;
+        __syncthreads();
+        // ---- every position: best match and match list
+        for (uint32_t pos0 = 0; pos0 < len; pos0 += HCS_SEARCH) {
+            const uint32_t ns = len - pos0 < HCS_SEARCH ? len - pos0 : HCS_SEARCH;
+            hcs_search<true>(sm, len, prm, pos0, ns, lists);
+            __syncthreads();
+            for (uint32_t i = tid; i < ns; i += HCS_THREADS) gbest[pos0 + i] = sm.w.res[i];
+            if (tid == 0) sm.c_search_next = 0;
+            __syncthreads();
+        }
+        // ---- blocks
+        uint32_t block_start = 0;
+        do {
+            // pass 1: greedy parse (BlockSplitStats) -> end of the block, histograms for the costs
+            for (uint32_t i = tid; i < 288; i += HCS_THREADS) sm.litlen_freq[i] = 0;
+            if (tid < 32) sm.offset_freq[tid] = 0;
+            if (tid < 14) { sm.new_obs[tid] = 0; sm.obs[tid] = 0; }
+            if (tid == 0) { sm.num_new = 0; sm.num_obs = 0; }
+            __syncthreads();
+            uint32_t block_end = len;
+            for (uint32_t entry = block_start; entry < len; ) {
+                const uint32_t wvalid = len - entry < HCS_W ? len - entry : HCS_W;
+                const uint32_t nload = len - entry < HCS_SEARCH ? len - entry : HCS_SEARCH;
+                for (uint32_t i = tid; i < nload; i += HCS_THREADS) sm.w.res[i] = gbest[entry + i];
+                __syncthreads();
+                hcs_steps_greedy(sm, len, prm, entry, wvalid);
+                hcs_parse_window(sm, len, entry, wvalid, block_start, 0, recs, true);
+                if (sm.c_split) { block_end = entry + sm.c_pc; break; }
+                for (uint32_t i = tid; i < 320; i += HCS_THREADS) {
+                    if (i < 288) sm.litlen_freq[i] += sm.freq_b[i];
+                    else sm.offset_freq[i - 288] += sm.freq_b[i];
+                }
+                if (tid < 14) sm.new_obs[tid] += sm.obs_b[tid];
+                if (tid == 0) sm.num_new += sm.cnt_b;
+                const uint32_t next_entry = entry + sm.c_next_entry;
+                __syncthreads();
+                entry = next_entry;
+            }
+            // symbol costs from the greedy histograms (update_costs, :2209-2224); a symbol the greedy
+            // pass never produced costs what a rare symbol would
+            if (tid == 0) sm.litlen_freq[256]++;
+            __syncthreads();
+            make_huffman_code_cta(288, 14, sm.litlen_freq, sm.litlen_len, sm.enc.litlen_code, sm.enc.scratch);
+            make_huffman_code_cta(32, 15, sm.offset_freq, sm.offset_len, sm.enc.offset_code, sm.enc.scratch);
+            for (uint32_t i = tid; i < 256 + 260 + 32; i += HCS_THREADS) {
+                if (i < 256) sm.dp.lit_cost[i] = sm.litlen_len[i] ? sm.litlen_len[i] : 12;
+                else if (i < 256 + 260) {
+                    const uint32_t l = i - 256;
+                    uint32_t c = 0;
+                    if (l >= 3 && l <= 258) {
+                        unsigned slot = length_slot_of(l), lb, le;
+                        length_slot_info(slot, lb, le);
+                        c = (sm.litlen_len[257 + slot] ? sm.litlen_len[257 + slot] : 10) + le;
+                    }
+                    sm.dp.len_cost[l] = (uint8_t)c;
+                } else {
+                    const uint32_t slot = i - 516;
+                    unsigned ob_, oe;
+                    offset_slot_info(slot < 30 ? slot : 29, ob_, oe);
+                    sm.dp.slot_cost[slot] = (uint8_t)((sm.offset_len[slot] ? sm.offset_len[slot] : 8) + oe);
+                }
+            }
+            __syncthreads();
+            // pass 2: cost to the end of the block, backwards.  The match lists of 504 positions are staged
+            // in shared memory by everybody, warp 0 walks them three positions per step, everybody writes
+            // the chunk's choices out.
+            if (tid == 0) sm.dp.ring[block_end & 511u] = 0;
+            for (uint32_t chi = block_end; chi > block_start; ) {
+                const uint32_t clo = chi - block_start > HCS_DP_CHUNK ? chi - HCS_DP_CHUNK : block_start;
+                for (uint32_t i = tid; i < (chi - clo) * 2; i += HCS_THREADS)
+                    reinterpret_cast<uint4 *>(sm.dp.lst)[i] = reinterpret_cast<const uint4 *>(lists + (size_t)clo * HCS_NLIST)[i];
+                __syncthreads();
+                if (warp == 0) {
+                    const uint32_t g = lane >> 3, k = lane & 7u;
+                    for (uint32_t hi = chi; hi > clo; hi = hi - clo > 3 ? hi - 3 : clo) {
+                        const uint32_t p = hi - 1 - g;                  // this lane's position (groups 0..2)
+                        const bool mine = g < 3 && hi >= clo + 1 + g;
+                        const uint32_t e = mine ? sm.dp.lst[(p - clo) * 8 + k] : 0u;
+                        // (the idle fourth group fetches the literal costs of the three positions)
+                        uint32_t litc = 0;
+                        if (g == 3 && k < 3 && hi >= clo + 1 + k) litc = sm.dp.lit_cost[sm.in[hi - 1 - k]];
+                        // entry k stands for every length above entry k - 1's up to its own, at its offset: the
+                        // lane tries its own length and up to NOS_SHORTER shorter ones (the reference's DP only
+                        // relaxes the list lengths themselves, src/compress/mod.rs:1683-1700; trying the shorter
+                        // ones as well makes up for what a chain walk finds less than the tree search)
+                        const uint32_t e_prev = __shfl_up_sync(BDF_FULL_MASK, e, 1);
+                        uint32_t v = NOS_INF << 4, vlen = 0;
+                        if (e) {
+                            const uint32_t l = e & 0xFFFFu, off = e >> 16;
+                            const uint32_t lmin0 = k ? (e_prev & 0xFFFFu) + 1u : 3u;
+                            const uint32_t lmin = l > lmin0 + NOS_SHORTER ? l - NOS_SHORTER : lmin0;
+                            const uint32_t sc = sm.dp.slot_cost[offset_slot_of(off)];
+#pragma unroll
+                            for (uint32_t d = 0; d <= NOS_SHORTER; d++) {
+                                const uint32_t t = l - d;
+                                if (t >= lmin && t <= l && p + t <= block_end) {
+                                    const uint32_t c = (sm.dp.len_cost[t] + sc + sm.dp.ring[(p + t) & 511u]) << 4 | k;
+                                    if (c < v) { v = c; vlen = t; }
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int d = 1; d < 8; d <<= 1) {
+                            const uint32_t t = __shfl_xor_sync(BDF_FULL_MASK, v, d);
+                            v = t < v ? t : v;
+                        }
+                        const uint32_t m0 = __shfl_sync(BDF_FULL_MASK, v, 0), m1 = __shfl_sync(BDF_FULL_MASK, v, 8), m2 = __shfl_sync(BDF_FULL_MASK, v, 16);
+                        const uint32_t ew = (e & 0xFFFF0000u) | vlen;                   // this lane's best (length, offset)
+                        const uint32_t w0 = __shfl_sync(BDF_FULL_MASK, ew, m0 & 7u), w1 = __shfl_sync(BDF_FULL_MASK, ew, 8 + (m1 & 7u)),
+                                       w2 = __shfl_sync(BDF_FULL_MASK, ew, 16 + (m2 & 7u));
+                        const uint32_t l0 = __shfl_sync(BDF_FULL_MASK, litc, 24), l1 = __shfl_sync(BDF_FULL_MASK, litc, 25),
+                                       l2 = __shfl_sync(BDF_FULL_MASK, litc, 26);
+                        if (lane == 0) {
+                            uint32_t c = sm.dp.ring[hi & 511u];
+                            const uint32_t mm[3] = {m0, m1, m2}, ww[3] = {w0, w1, w2}, ll[3] = {l0, l1, l2};
+#pragma unroll
+                            for (int j = 0; j < 3; j++) {
+                                if (hi >= clo + 1u + j) {
+                                    const uint32_t q = hi - 1 - j;
+                                    const uint32_t lit = c + ll[j];
+                                    const uint32_t mc = mm[j] >> 4;
+                                    uint32_t ch = 1u;
+                                    c = lit;
+                                    if (mc < lit) { c = mc; ch = ww[j]; }
+                                    sm.dp.ring[q & 511u] = c;
+                                    sm.dp.ch[q - clo] = ch;
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                __syncthreads();
+                for (uint32_t i = tid; i < chi - clo; i += HCS_THREADS) choice[clo + i] = sm.dp.ch[i];
+                __syncthreads();
+                chi = clo;
+            }
+            // pass 3: the parse along the choices: records and the block's final histograms
+            for (uint32_t i = tid; i < 288; i += HCS_THREADS) sm.litlen_freq[i] = 0;
+            if (tid < 32) sm.offset_freq[tid] = 0;
+            __syncthreads();
+            uint32_t nrec = 0;
+            for (uint32_t entry = block_start; entry < block_end; ) {
+                const uint32_t wvalid = block_end - entry < HCS_W ? block_end - entry : HCS_W;
+                for (uint32_t i = tid; i < wvalid; i += HCS_THREADS) {
+                    const uint32_t ch = choice[entry + i], l = ch & 0xFFFFu;
+                    sm.w.res[i] = ch;
+                    sm.w.nxt[i] = (uint16_t)(l == 1 ? 1u : (l | 1u << 11));
+                }
+                __syncthreads();
+                hcs_parse_window(sm, block_end, entry, wvalid, block_start, nrec, recs, false);
+                nrec += sm.c_win_rec;
+                const uint32_t next_entry = entry + sm.c_next_entry;
+                __syncthreads();
+                entry = next_entry;
+            }
+            const bool is_final = block_end >= len && (uflags & UNIT_FINISH);
+            hcs_encode_block<false>(sm, sink, recs, 0, nrec, is_final);
+            block_start = block_end;
+        } while (block_start < len);
+        hcs_finish_stream<false>(sm, a, idx, gin, len, out, hdr, uflags);
     }
 }
 

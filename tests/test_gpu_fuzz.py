@@ -8,6 +8,7 @@ import pytest
 
 import corpus
 import oracle_lib as o
+import tier
 
 pytestmark = pytest.mark.gpu
 WBITS = {0: -15, 1: 15, 2: 31}
@@ -61,14 +62,17 @@ def test_compress_random_batches_match_oracle(engine, seed):
                 assert zlib.decompress(g, WBITS[fmt]) == s
 
 
-def test_near_optimal_random_batch_matches_oracle(engine):
+def test_near_optimal_random_batch_within_tolerance(engine):
     rng = np.random.default_rng(7)
     for level in (10, 11, 12):
         bufs = [random_buffer(rng, 30000) for _ in range(12)]
         got = engine.BatchCompressor(level).compress_batch(bufs)
+        pairs = []
         for g, s in zip(got, bufs):
             exp = o.compress(s, level)
-            assert g == (exp if exp is not None else b""), (level, len(s))
+            tier.check_stream(g, s, exp, level, 0)
+            pairs.append((g, exp))
+        tier.check_total(pairs, level)
 
 
 @pytest.mark.parametrize("seed", [3, 4])

@@ -9,6 +9,7 @@ import pytest
 
 import corpus
 import oracle_lib as o
+import tier
 
 pytestmark = pytest.mark.gpu
 
@@ -27,14 +28,16 @@ def batch():
 def test_three_compress_entry_points(engine, level, fmt):
     bufs = batch()
     c = engine.BatchCompressor(level, format=fmt)
-    exp = [o.compress(b, level, fmt) or b"" for b in bufs]
-    assert c.compress_batch(bufs) == exp                   # scattered input, packed result
-    assert c.compress_batch_slots(bufs) == exp             # flat input, bound-spaced slots
+    exp = [o.compress(b, level, fmt) for b in bufs]
+    first = c.compress_batch(bufs)                         # scattered input, packed result
+    for g, b, e in zip(first, bufs, exp):
+        tier.check_stream(g, b, e, level, fmt)
+    assert c.compress_batch_slots(bufs) == first           # flat input, bound-spaced slots
     flat, off = engine.flatten(bufs)
     out, out_off, status = c.compress_dense(flat, off)      # flat input, packed result
     got = [out[int(out_off[i]):int(out_off[i + 1])].tobytes() for i in range(len(bufs))]
-    assert got == exp
-    assert all((status[i] == 0) == (o.compress(b, level, fmt) is not None) for i, b in enumerate(bufs))
+    assert got == first
+    assert all((status[i] == 0) == (first[i] != b"" or (len(b) == 0 and level == 0)) for i, b in enumerate(bufs))
 
 
 def test_scattered_input_larger_than_a_staging_buffer(engine):
@@ -139,8 +142,8 @@ def test_two_caller_streams_do_not_share_scratch(engine, level):
     for d, (bufs, ooff) in zip(keep, outs):
         size = d["size"].cpu().numpy(); stat = d["stat"].cpu().numpy(); out = d["out"].cpu().numpy()
         for i, b in enumerate(bufs):
-            exp = o.compress(b, level)
-            assert stat[i] == 0 and out[int(ooff[i]):int(ooff[i]) + int(size[i])].tobytes() == exp, i
+            assert stat[i] == 0, i
+            tier.check_stream(out[int(ooff[i]):int(ooff[i]) + int(size[i])].tobytes(), b, o.compress(b, level), level, 0, i)
     est = d_est.cpu().numpy()
     assert (d_est_stat.cpu().numpy() == 0).all()
     assert [int(v) for v in est[:20]] == [o.compress_to_size(b, level) for b in sets[0][:20]]

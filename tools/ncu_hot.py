@@ -9,10 +9,11 @@ tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, check=True, capture_output=True)
 cub = glob.glob(tmp + "/*.cubin")[0]
 txt = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout.split("\n")
-inside, cur, dis = False, None, []
+inside, cur, secs = False, None, {}
 for line in txt:
     if line.startswith(".text."):
-        inside = kern in line
+        inside = kern.split("<")[0].split("IL")[0] in line
+        name = line.strip()
         continue
     if not inside:
         continue
@@ -22,7 +23,7 @@ for line in txt:
         continue
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
     if m:
-        dis.append((cur, m.group(2)))
+        secs.setdefault(name, []).append((cur, m.group(2)))
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 blocks, b = [], None
@@ -37,8 +38,10 @@ hdr, prof = blk["rows"][0], blk["rows"][1:]
 ie, it, iss = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
 isrc = hdr.index("Source")
 prof = [r for r in prof if len(r) > ie]
-assert len(prof) == len(dis), (len(prof), len(dis))
-assert all(d[1].split()[0] == p[isrc].split()[0] for d, p in zip(dis, prof)), "SASS differs: profile another build?"
+# the template instance that was profiled: same length, same opcodes
+dis = next((d for d in secs.values() if len(d) == len(prof) and
+            all(x[1].split()[0] == p[isrc].split()[0] for x, p in zip(d, prof))), None)
+assert dis is not None, ("no section of the .so matches the profiled SASS", len(prof), {k: len(v) for k, v in secs.items()})
 agg, smp, thr = collections.Counter(), collections.Counter(), collections.Counter()
 for d, p in zip(dis, prof):
     agg[d[0]] += int(p[ie]); smp[d[0]] += int(p[iss]); thr[d[0]] += int(p[it])
