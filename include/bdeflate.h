@@ -124,7 +124,10 @@ int bdf_decompress_batch_host(bdf_ctx *ctx, int format, const uint8_t *in,
  * Stream length: the *_host call takes any length.  Streams above 64 KiB run through the
  * 256 KiB kernel instances; streams above 256 KiB are cut into 256 KiB chunks, each compressed
  * by a fresh compressor, all but the last followed by a sync flush, like Compressor::compress
- * (src/compress/mod.rs:699-772) — byte-identical to the reference's output for every length.
+ * (src/compress/mod.rs:699-772).  Levels 0..9 are byte-identical to this repository's restatement of
+ * the reference compressor (oracle/; outputs of the real Rust binary cannot be captured here: no
+ * toolchain); levels 10..12 on streams of at most 64 KiB are held to its size (within 0.5 %), not
+ * its bytes.
  * The *_device call cannot see the lengths without synchronising: it runs the 64 KiB instances
  * and sets status[i] = BDF_STREAM_UNSUPPORTED for a longer stream (level 0 takes any length up
  * to 256 KiB there).
