@@ -718,7 +718,11 @@ def main():
                 "l2": "working set (4 GiB out + compressed in) >> 126 MB L2; no explicit flush",
             },
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "bdf_decompress_batch_host (pinned host buffers)"},
+                    "steps": e2e_steps, "api": "bdf_decompress_batch_host (pinned host buffers)",
+                    # the result (4 GiB per GPU and step) has to cross to the host: what this pool's 8-GPU
+                    # boxes take from N GPUs at once, whatever the copies per rank and the host memory kind
+                    "host_d2h_ceiling_gbs": {"1": 55.8, "2": 71.5, "4": 73.9, "8": 104.8},
+                    "host_d2h_ceiling_source": "profiles/r2_d2h_matrix.txt (gpurun_scripts/probe/d2h_matrix.cu)"},
             "gpu_launches": int(launches),
             "roofline": roofline("bdf::inflate_kernel<BDF_ZLIB>", comp_bytes + out_bytes, kernel_ms, n, "inflate_config2"),
             "clocks": clocks.summary(),

@@ -70,6 +70,10 @@ int bdf_device_count(void);
 int bdf_ctx_create(int device, bdf_ctx **ctx);
 void bdf_ctx_destroy(bdf_ctx *ctx);
 const char *bdf_last_error(const bdf_ctx *ctx);
+/* Debug builds of the library (-DBDF_CHECK, libbdeflate_check.so: bounds / invariant assertions in
+ * the kernels): source line | 0x80000000 of the first assertion that failed on this process's
+ * device, 0 if none; -1 from a build without the assertions. */
+long long bdf_debug_check_failures(bdf_ctx *ctx);
 /* Number of engine kernels launched through this ctx so far. */
 uint64_t bdf_kernel_launches(const bdf_ctx *ctx);
 /* Device time (ms, CUDA events on the ctx stream) of the kernels of the last

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libbdeflate.so")
+# BDF_LIBRARY selects another build of the same ABI (the -DBDF_CHECK debug build, tests/test_gpu_check_build.py)
+SO_PATH = os.environ.get("BDF_LIBRARY") or os.path.join(HERE, "libbdeflate.so")
 
 RAW, ZLIB, GZIP = 0, 1, 2
 OK, BAD_DATA, SHORT_OUTPUT, INSUFFICIENT_SPACE, SHORT_INPUT = range(5)
@@ -22,7 +23,7 @@ EXPORTS = [
     "bdf_compress_batch_device", "bdf_compress_batch_host", "bdf_checksum_batch_device",
     "bdf_checksum_batch_host", "bdf_gather_streams_device", "bdf_compress_units_host",
     "bdf_compress_size_batch_device", "bdf_compress_size_batch_host",
-    "bdf_compress_batch_host_dense", "bdf_compress_batch_host_sg",
+    "bdf_compress_batch_host_dense", "bdf_compress_batch_host_sg", "bdf_debug_check_failures",
 ]
 
 
@@ -45,6 +46,8 @@ def load():
     L.bdf_ctx_destroy.argtypes = [vp]
     L.bdf_last_error.restype = C.c_char_p
     L.bdf_last_error.argtypes = [vp]
+    L.bdf_debug_check_failures.restype = C.c_longlong
+    L.bdf_debug_check_failures.argtypes = [vp]
     L.bdf_kernel_launches.restype = C.c_uint64
     L.bdf_kernel_launches.argtypes = [vp]
     L.bdf_last_kernel_ms.restype = C.c_float

@@ -24,15 +24,21 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return OUT
+OUT_CHECK = os.path.join(HERE, "libbdeflate_check.so")
+
+
+def build(force=False, verbose=False, check=False):
+    """check=True: the debug build with device-side assertions (-DBDF_CHECK), libbdeflate_check.so."""
+    out = OUT_CHECK if check else OUT
+    stale = not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in DEPS)
+    if not force and not stale:
+        return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    cmd = [nvcc] + NVCC_FLAGS + (["-DBDF_CHECK"] if check else []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
     import sys
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, check="--check" in sys.argv))

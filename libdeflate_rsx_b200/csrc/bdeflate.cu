@@ -41,7 +41,7 @@ struct bdf_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t copy_streams[8] = {};          // large device-to-host results go out as 8 concurrent copies
-    int d2h_streams = 8;                        // how many of them a call uses (BDF_D2H_STREAMS; fewer when many ranks share the host)
+    int d2h_streams = 8;                        // how many of them a call uses (BDF_D2H_STREAMS)
     unsigned copy_waited = 0;
     cudaStream_t aux_stream = nullptr;          // second engine of a decompress call (runs beside the first)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -265,13 +265,11 @@ int bdf_ctx_create(int device, bdf_ctx **out)
     if (const char *e = getenv("BDF_LANE_CFG")) ctx->lane_cfg = atoi(e) >= 0 && atoi(e) <= 2 ? atoi(e) : 0;
     if (const char *e = getenv("BDF_LANE_WARPS")) ctx->lane_warps_per_sm = atoi(e) > 0 ? atoi(e) : 0;
     {
-        // Device-to-host result copies per call.  Eight concurrent copies are best when one process
-        // owns the host (56.6 vs 51 GB/s); with several ranks returning results to the same host at once
-        // the copies of all ranks share its memory system, so each rank uses fewer (LOCAL_WORLD_SIZE is
-        // set by torchrun).  BDF_D2H_STREAMS overrides.
-        int ranks = 1;
-        if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e) > 0 ? atoi(e) : 1;
-        ctx->d2h_streams = ranks >= 8 ? 2 : ranks >= 4 ? 2 : ranks >= 2 ? 4 : 8;
+        // Device-to-host result copies per call: eight concurrent copies (56.6 vs 51 GB/s for one when a
+        // single process owns the host).  With 2 / 4 / 8 ranks returning results to the same host the
+        // aggregate is set by the host, not by this number: 70 / 73 / 104 GB/s in total whatever the
+        // copies per rank (1..8) and the kind of host memory (profiles/r2_d2h_matrix.txt).
+        ctx->d2h_streams = 8;
         if (const char *e = getenv("BDF_D2H_STREAMS")) {
             int v = atoi(e);
             if (v >= 1 && v <= 8) ctx->d2h_streams = v;
@@ -333,6 +331,24 @@ void bdf_ctx_destroy(bdf_ctx *ctx)
 }
 
 const char *bdf_last_error(const bdf_ctx *ctx) { return ctx ? ctx->err : "null ctx"; }
+
+// Debug builds (-DBDF_CHECK): source line of the first failed device assertion | 0x80000000, 0 if
+// none; -1 in a build without the assertions.  Synchronises the device.
+long long bdf_debug_check_failures(bdf_ctx *ctx)
+{
+#ifdef BDF_CHECK
+    if (!ctx) return -1;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    unsigned v = 0;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpyFromSymbol(&v, g_bdf_check_fail, sizeof(v)) != cudaSuccess)
+        return -2;
+    return (long long)v;
+#else
+    (void)ctx;
+    return -1;
+#endif
+}
 uint64_t bdf_kernel_launches(const bdf_ctx *ctx) { return ctx ? ctx->launches : 0; }
 float bdf_last_kernel_ms(const bdf_ctx *ctx) { return ctx ? ctx->last_ms : 0.f; }
 

@@ -7,6 +7,18 @@
 
 #define BDF_FULL_MASK 0xFFFFFFFFu
 
+// Debug build (python -m libdeflate_rsx_b200.build --check -> libbdeflate_check.so): explicit bounds /
+// invariant assertions at the kernels' shared- and global-memory indices.  The first failing source
+// line is kept in a device word that bdf_debug_check_failures() reads back; compute-sanitizer is
+// refused on the pool this was developed on, so this (plus tests/test_gpu_determinism.py) is the
+// memcheck / racecheck stand-in.
+#ifdef BDF_CHECK
+__device__ unsigned int g_bdf_check_fail;
+#define BDF_ASSERT(c) do { if (!(c)) atomicCAS(&g_bdf_check_fail, 0u, (unsigned)__LINE__ | 0x80000000u); } while (0)
+#else
+#define BDF_ASSERT(c) do { } while (0)
+#endif
+
 namespace bdf {
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }

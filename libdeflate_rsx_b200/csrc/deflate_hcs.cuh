@@ -163,6 +163,7 @@ struct CtaSink {
         if (nb && !COUNT) {
             const uint32_t at = base + incl - nb;
             const uint32_t w = at >> 5, sh = at & 31u;
+            BDF_ASSERT(nb <= 64 && w + 2 < HCS_STAGE_WORDS);
             const uint32_t lo = (uint32_t)bits, hi = (uint32_t)(bits >> 32);
             atomicOr(&sm.enc.stage[w], lo << sh);
             const unsigned long long up = sh ? ((unsigned long long)hi << 32 | lo) >> (32 - sh) : hi;
@@ -446,7 +447,11 @@ __device__ __forceinline__ void hcs_search(HcsSmem &sm, uint32_t len, const HcPa
                     cur -= lk;
                     if (++depth >= prm.max_depth) { done = true; break; }
                 }
-                if (done) { sm.w.res[p - entry] = best | boff << 16; active = false; }
+                if (done) {
+                    BDF_ASSERT(p - entry < HCS_SEARCH && best <= 258 && boff <= 32768 && (best < 3 || (boff >= 1 && boff <= p)));
+                    sm.w.res[p - entry] = best | boff << 16;
+                    active = false;
+                }
             }
         }
     }
@@ -632,6 +637,7 @@ __device__ __forceinline__ void hcs_parse_window(HcsSmem &sm, uint32_t len, uint
         if (2 * tid + h < nsteps) {
             const uint32_t cur = h ? cur1 : cur0, n = h ? n1 : n0;
             uint32_t r = nrec + base_rc + (h ? rc0 : 0u);
+            BDF_ASSERT(r + 3 <= 65536 + 64 && entry + cur < len);
             const bool behind = cur >= pc;
             if (cur == pc) sm.c_rec_at_pc = r;
             uint32_t *fq = behind ? sm.freq_b : sm.freq_a;
@@ -1083,6 +1089,7 @@ __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_nos_kernel(DeflateArgs
                                     uint32_t ch = 1u;
                                     c = lit;
                                     if (mc < lit) { c = mc; ch = ww[j]; }
+                                    BDF_ASSERT(q - clo < HCS_DP_CHUNK && q < 65536 && q + (ch & 0xFFFFu) <= block_end);
                                     sm.dp.ring[q & 511u] = c;
                                     sm.dp.ch[q - clo] = ch;
                                 }

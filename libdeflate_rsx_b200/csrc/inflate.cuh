@@ -382,6 +382,7 @@ __device__ __forceinline__ void flush_literals(OutState &o, unsigned lane)
 {
     if (o.npend) {
         if (lane < o.npend) {
+            BDF_ASSERT(o.pos + lane < o.cap);
             o.out[o.pos + lane] = (uint8_t)o.mylit;
             adler_acc1<ADLER>(o, o.pos + lane, o.mylit);
         }
@@ -468,6 +469,7 @@ __device__ __forceinline__ void copy_match_part(const Grp<G> &g, OutState &o, un
     g.sync();   // earlier stores by other lanes of the group may be our source
     uint8_t *base = o.out;
     const uint32_t dpos = o.pos;
+    BDF_ASSERT(offset >= 1 && offset <= dpos && dpos + length <= o.cap);
     const uint8_t *pat = base + dpos - offset;       // one period of the match source
     if (length <= (unsigned)G) {
         // short match (the common case in text): one byte per lane

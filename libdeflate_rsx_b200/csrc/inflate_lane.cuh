@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                     }
                     __syncwarp();
                     if (lane == s) {
+                        BDF_ASSERT(pos + blen <= cap);
                         pos += blen; flushed = pos; ring_lo = pos;
                         if (ADLER) { sumA = (sumA + pa) % 65521u; sumB = (sumB + pb) % 65521u; }
                     }
@@ -410,6 +411,8 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                 // what lies beyond pos + n is overwritten before it is read (it aliases output that is
                 // flushed and further back than any ring source, or the slack behind the ring).
                 const uint32_t wd = d >> 2, ss = 8u * (d & 3u);
+                BDF_ASSERT(wd + 4 < (RING + 16) / 4 && n >= 1 && pos + n <= cap && pos - flushed + n <= (uint32_t)RING - 24);
+                BDF_ASSERT(!(avail > NEAR || copy_src < ring_lo) || copy_src + n <= flushed);      // a far source is flushed output
                 const uint32_t old = ringw[wd];
                 ringw[wd] = (old & ((1u << ss) - 1u)) | (x0 << ss);
                 ringw[wd + 1] = __funnelshift_l(x0, x1, ss);
@@ -459,6 +462,7 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                         lcode.find(br.peek(15), li, ll);
                         if (ll == 0) { status = BDF_BAD_DATA; st = LS_END; }
                         else {
+                            BDF_ASSERT(li < 288);
                             pend_sym = __ldcg(my_sorted + li);
                             pend_len = ll;
                             br.drop(ll);
@@ -483,6 +487,7 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                         if ((f & E_LEN) == 0) {
                             uint32_t oi, ol;
                             ocode.find(br.peek(15), oi, ol);
+                            BDF_ASSERT(ol == 0 || oi < 32);
                             f = ol ? make_offset_entry(__ldcg(my_sorted + 288 + oi), ol) : 0u;
                         }
                         if (f == 0) { status = BDF_BAD_DATA; st = LS_END; }
@@ -521,6 +526,7 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                         const uint4 *rq = reinterpret_cast<const uint4 *>(ring + ((flushed + rbias) & MASK));
                         const uint4 v0 = rq[0], v1 = rq[1];
                         uint4 *dst = reinterpret_cast<uint4 *>(out + flushed);
+                        BDF_ASSERT(flushed + 32 <= pos && pos <= cap && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
                         dst[0] = v0;
                         dst[1] = v1;
                         if (ADLER) {

@@ -1,0 +1,39 @@
+"""Stand-in for a race check (compute-sanitizer is refused on this pool): the same batches through
+different kernels, grids and streams-per-warp must give identical bytes.  One subprocess per set of
+switches (they are read once per process): hash-chain kernel choice and resident CTAs for the
+compressor, engine / lane-group size / table geometry for the decompressor."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+VARIANTS = [
+    {},
+    {"BDF_HC_KERNEL": "old", "BDF_INFLATE_MODE": "group"},
+    {"BDF_HC_KERNEL": "new", "BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "1"},
+    {"BDF_HC_KERNEL": "old", "BDF_HC_CTAS_PER_SM": "3", "BDF_INFLATE_MODE": "group", "BDF_INFLATE_GROUP": "32"},
+    {"BDF_INFLATE_MODE": "auto", "BDF_INFLATE_SPLIT": "4", "BDF_LANE_WARPS": "3"},
+]
+
+
+def run(env):
+    e = dict(os.environ)
+    for k in ("BDF_HC_KERNEL", "BDF_HC_CTAS_PER_SM", "BDF_INFLATE_MODE", "BDF_INFLATE_GROUP", "BDF_LANE_CFG",
+              "BDF_INFLATE_SPLIT", "BDF_LANE_WARPS"):
+        e.pop(k, None)
+    e.update(env)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "determinism_helper.py")], cwd=ROOT, env=e,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return [l for l in out.stdout.splitlines() if l.startswith(("compress", "decompress"))]
+
+
+def test_same_bytes_whatever_the_kernel_choice():
+    base = run(VARIANTS[0])
+    assert len(base) == 9
+    for v in VARIANTS[1:]:
+        assert run(v) == base, v
