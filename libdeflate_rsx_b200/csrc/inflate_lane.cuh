@@ -173,7 +173,6 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
     uint32_t at = 0;                 // offset of the DEFLATE data
     uint32_t pos = 0, cap = 0, flushed = 0, ring_lo = 0, rbias = 0;
     uint32_t copy_rem = 0, copy_src = 0;
-    uint32_t pend_sym = 0, pend_len = 0;    // litlen symbol of a long codeword, on its way from the symbol list
     uint64_t pfa = 0, pfb = 0, pfc = 0;     // the 24 aligned bytes around a far source, requested one round ahead
     bool pf_valid = false, final_blk = false;
     uint32_t sumA = 0;
@@ -274,7 +273,7 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                             sp = a.in + o0;
                             out = a.out + a.out_off[my];
                             cap = cap64 > INFLATE_CAP_MAX ? INFLATE_CAP_MAX : (uint32_t)cap64;
-                            pos = 0; flushed = 0; ring_lo = 0; copy_rem = 0; pend_len = 0; pf_valid = false; final_blk = false;
+                            pos = 0; flushed = 0; ring_lo = 0; copy_rem = 0; pf_valid = false; final_blk = false;
                             sumA = 0; sumB = 0;
                             rbias = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 31u);
                             status = BDF_OK;
@@ -426,23 +425,13 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                 if (n < avail) copy_src += n;
                 if (copy_rem != 0 && (avail > NEAR || copy_src < ring_lo)) prefetch(copy_src, copy_rem);
             }
-            // ---- A: one symbol: up to two literals, or a length / offset pair.  A litlen codeword longer
-            // than the table costs a load from the lane's symbol list in global memory: like the far
-            // copies it is issued in one round (the codeword length is known, the bits are dropped) and
-            // the symbol is dispatched in the next.
+            // ---- A: one symbol: up to two literals, or a length / offset pair
             if (st == LS_RUN && copy_rem == 0 && pos - flushed <= DECODE_MAX) {
-                uint32_t e = 0;
-                bool have = false;          // a symbol to dispatch whose codeword bits are already dropped
-                if (pend_len) {
-                    e = make_litlen_entry(pend_sym, pend_len);
-                    pend_len = 0;
-                    have = true;
-                } else if (br.left <= 32 && br.widx > br.nwords + 2) {
-                    // more than two zero-fill words loaded: the stream ended inside this block
-                    status = BDF_SHORT_INPUT; st = LS_END;
-                } else {
+                // more than two zero-fill words loaded: the stream ended inside this block
+                if (br.left <= 32 && br.widx > br.nwords + 2) { status = BDF_SHORT_INPUT; st = LS_END; }
+                else {
                     lane_refill(br);
-                    e = T.lit_tab[br.peek(LTB)];
+                    uint32_t e = T.lit_tab[br.peek(LTB)];
                     if (e & LITFLAG) {
                         if (pos >= cap) { status = BDF_INSUFFICIENT_SPACE; st = LS_END; }
                         else {
@@ -457,50 +446,45 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                                 br.drop(e & E_LEN);
                             }
                         }
-                    } else if ((e & E_LEN) == 0) {
-                        uint32_t li, ll;
-                        lcode.find(br.peek(15), li, ll);
-                        if (ll == 0) { status = BDF_BAD_DATA; st = LS_END; }
-                        else {
-                            BDF_ASSERT(li < 288);
-                            pend_sym = __ldcg(my_sorted + li);
-                            pend_len = ll;
-                            br.drop(ll);
-                        }
                     } else {
-                        br.drop(e & E_LEN);
-                        have = true;
-                    }
-                }
-                if (have) {
-                    const uint32_t kind = e & K_MASK;
-                    if (kind == K_LIT) {                       // a literal with a codeword longer than the table
-                        if (pos >= cap) { status = BDF_INSUFFICIENT_SPACE; st = LS_END; }
-                        else { ring[(pos + rbias) & MASK] = (uint8_t)(e >> E_VAL); pos++; }
-                    } else if (kind == K_EOB) {
-                        status = br.overrun() ? BDF_SHORT_INPUT : BDF_OK;
-                        st = (status == BDF_OK && !final_blk) ? LS_HDR : LS_END;
-                    } else {
-                        const unsigned length = take_length(br, e);
-                        lane_refill(br);
-                        uint32_t f = T.off_tab[br.peek(OTB)];
-                        if ((f & E_LEN) == 0) {
-                            uint32_t oi, ol;
-                            ocode.find(br.peek(15), oi, ol);
-                            BDF_ASSERT(ol == 0 || oi < 32);
-                            f = ol ? make_offset_entry(__ldcg(my_sorted + 288 + oi), ol) : 0u;
+                        if ((e & E_LEN) == 0) {
+                            uint32_t li, ll;
+                            lcode.find(br.peek(15), li, ll);
+                            BDF_ASSERT(ll == 0 || li < 288);
+                            e = ll ? make_litlen_entry(__ldcg(my_sorted + li), ll) : 0u;
                         }
-                        if (f == 0) { status = BDF_BAD_DATA; st = LS_END; }
-                        else {
-                            br.drop(f & E_LEN);
-                            const unsigned offset = take_offset(br, f);
-                            if (offset > pos) { status = BDF_BAD_DATA; st = LS_END; }
-                            else if (length > cap - pos) { status = BDF_INSUFFICIENT_SPACE; st = LS_END; }
+                        const uint32_t kind = e & K_MASK;
+                        if (e == 0) { status = BDF_BAD_DATA; st = LS_END; }
+                        else if (kind == K_LIT) {                  // a literal with a codeword longer than the table
+                            if (pos >= cap) { status = BDF_INSUFFICIENT_SPACE; st = LS_END; }
+                            else { ring[(pos + rbias) & MASK] = (uint8_t)(e >> E_VAL); pos++; br.drop(e & E_LEN); }
+                        } else if (kind == K_EOB) {
+                            br.drop(e & E_LEN);
+                            status = br.overrun() ? BDF_SHORT_INPUT : BDF_OK;
+                            st = (status == BDF_OK && !final_blk) ? LS_HDR : LS_END;
+                        } else {
+                            br.drop(e & E_LEN);
+                            const unsigned length = take_length(br, e);
+                            lane_refill(br);
+                            uint32_t f = T.off_tab[br.peek(OTB)];
+                            if ((f & E_LEN) == 0) {
+                                uint32_t oi, ol;
+                                ocode.find(br.peek(15), oi, ol);
+                                BDF_ASSERT(ol == 0 || oi < 32);
+                                f = ol ? make_offset_entry(__ldcg(my_sorted + 288 + oi), ol) : 0u;
+                            }
+                            if (f == 0) { status = BDF_BAD_DATA; st = LS_END; }
                             else {
-                                copy_rem = length;
-                                copy_src = pos - offset;
-                                pf_valid = false;
-                                if (offset > NEAR || copy_src < ring_lo) prefetch(copy_src, length);
+                                br.drop(f & E_LEN);
+                                const unsigned offset = take_offset(br, f);
+                                if (offset > pos) { status = BDF_BAD_DATA; st = LS_END; }
+                                else if (length > cap - pos) { status = BDF_INSUFFICIENT_SPACE; st = LS_END; }
+                                else {
+                                    copy_rem = length;
+                                    copy_src = pos - offset;
+                                    pf_valid = false;
+                                    if (offset > NEAR || copy_src < ring_lo) prefetch(copy_src, length);
+                                }
                             }
                         }
                     }
