@@ -16,7 +16,11 @@ import libdeflate_rsx_b200 as b
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 want = sys.argv[2:] or ["group", "lane0", "lane1", "auto"]
 ENV = {"group": {"BDF_INFLATE_MODE": "group"}, "lane0": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "0"},
-       "lane1": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "1"}, "lane2": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "2"}, "auto": {"BDF_INFLATE_MODE": "auto"}}
+       "lane1": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "1"}, "lane2": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "2"}, "auto": {"BDF_INFLATE_MODE": "auto"},
+       # the same without the first-block header pre-pass (inflate_prehdr.cuh)
+       "auto_nopre": {"BDF_INFLATE_MODE": "auto", "BDF_INFLATE_PREHDR": "0"},
+       "group_nopre": {"BDF_INFLATE_MODE": "group", "BDF_INFLATE_PREHDR": "0"},
+       "lane0_nopre": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "0", "BDF_INFLATE_PREHDR": "0"}}
 dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(dev)
 torch.cuda.set_stream(stream)
@@ -27,7 +31,7 @@ KINDS = {
 }
 ctxs = {}
 for m in want:
-    for k in ("BDF_INFLATE_MODE", "BDF_LANE_CFG"):
+    for k in ("BDF_INFLATE_MODE", "BDF_LANE_CFG", "BDF_INFLATE_PREHDR"):
         os.environ.pop(k, None)
     os.environ.update(ENV[m])
     ctxs[m] = b.Context(0)

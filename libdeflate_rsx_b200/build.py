@@ -27,18 +27,22 @@ def needs_build():
 OUT_CHECK = os.path.join(HERE, "libbdeflate_check.so")
 
 
-def build(force=False, verbose=False, check=False):
-    """check=True: the debug build with device-side assertions (-DBDF_CHECK), libbdeflate_check.so."""
-    out = OUT_CHECK if check else OUT
+def build(force=False, verbose=False, check=False, defines=(), out=None):
+    """check=True: the debug build with device-side assertions (-DBDF_CHECK), libbdeflate_check.so.
+    defines / out: an experiment build (-DNAME=VALUE ...) under another file name, loaded with BDF_LIBRARY."""
+    out = os.path.join(HERE, out) if out else (OUT_CHECK if check else OUT)
     stale = not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in DEPS)
     if not force and not stale:
         return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-DBDF_CHECK"] if check else []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
+    cmd = [nvcc] + NVCC_FLAGS + (["-DBDF_CHECK"] if check else []) + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
     subprocess.check_call(cmd)
     return out
 
 
 if __name__ == "__main__":
     import sys
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, check="--check" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, check="--check" in sys.argv, defines=defs,
+                out=outs[0] if outs else None))

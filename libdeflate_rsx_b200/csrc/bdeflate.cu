@@ -19,6 +19,7 @@
 #include "checksum.cuh"
 #include "inflate.cuh"
 #include "inflate_lane.cuh"
+#include "inflate_prehdr.cuh"
 #include "deflate.cuh"
 
 namespace {
@@ -62,9 +63,10 @@ struct bdf_ctx {
     int inflate_mode = 0;                       // 0 = both engines, split by expansion ratio; 1 = lane groups only; 2 = lane per stream only (BDF_INFLATE_MODE)
     int inflate_split = 16;                     // expansion ratio from which a stream goes to the lane-group kernel (BDF_INFLATE_SPLIT)
     int lane_cfg = 0;                           // direct-table bits of inflate_lane_kernel: 0 = (8, 7), 7 warps / SM; 1 = (9, 6), 5 warps / SM; 2 = (8, 6), 8 warps / SM (BDF_LANE_CFG)
+    int inflate_prehdr = 1;                     // first-block headers decoded by inflate_prehdr_kernel ahead of the engines (BDF_INFLATE_PREHDR=0: off)
     int lane_warps_per_sm = 0;                  // cap on resident warps of inflate_lane_kernel, 0 = what fits (BDF_LANE_WARPS)
     bdf::DeflateScratch deflate_scratch;
-    DevBuf in, out, in_off, out_off, max_out, out_size, status, checksum, lane_scratch, dense, dense_off;
+    DevBuf in, out, in_off, out_off, max_out, out_size, status, checksum, lane_scratch, dense, dense_off, hdr_rows, hdr_meta;
     void *h_stage[2] = {nullptr, nullptr};      // pinned: packing buffers of a scattered input
     size_t h_stage_cap[2] = {0, 0};
     void *h_result = nullptr;                   // pinned: dense result on its way to bound-spaced slots
@@ -263,6 +265,7 @@ int bdf_ctx_create(int device, bdf_ctx **out)
         if (v >= 1 && v <= 1032) ctx->inflate_split = v;
     }
     if (const char *e = getenv("BDF_LANE_CFG")) ctx->lane_cfg = atoi(e) >= 0 && atoi(e) <= 2 ? atoi(e) : 0;
+    if (const char *e = getenv("BDF_INFLATE_PREHDR")) ctx->inflate_prehdr = atoi(e) != 0;
     if (const char *e = getenv("BDF_LANE_WARPS")) ctx->lane_warps_per_sm = atoi(e) > 0 ? atoi(e) : 0;
     {
         // Device-to-host result copies per call: eight concurrent copies (56.6 vs 51 GB/s for one when a
@@ -308,7 +311,7 @@ void bdf_ctx_destroy(bdf_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->in, &ctx->out, &ctx->in_off, &ctx->out_off, &ctx->max_out,
-                      &ctx->out_size, &ctx->status, &ctx->checksum, &ctx->lane_scratch, &ctx->dense, &ctx->dense_off, &ctx->u_in_off, &ctx->u_tmp_off,
+                      &ctx->out_size, &ctx->status, &ctx->checksum, &ctx->lane_scratch, &ctx->dense, &ctx->dense_off, &ctx->hdr_rows, &ctx->hdr_meta, &ctx->u_in_off, &ctx->u_tmp_off,
                       &ctx->u_size, &ctx->u_status, &ctx->u_flags, &ctx->u_begin, &ctx->u_tmp};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -461,6 +464,28 @@ static int decompress_device_locked(bdf_ctx *ctx, int format, const uint8_t *in,
     a.work_counter = next_counter(ctx, s);
     a.work_counter2 = next_counter(ctx, s);
     if (!a.work_counter || !a.work_counter2) return fail(ctx, BDF_E_CUDA, "cudaMemsetAsync(work counter)");
+    a.hdr_rows = nullptr;
+    a.hdr_meta = nullptr;
+    if (ctx->inflate_prehdr) {
+        // every stream starts with a block header: decode the first one of the whole batch lane-parallel
+        if ((rc = ensure(ctx, ctx->hdr_rows, n * (size_t)bdf::PREHDR_ROW_BYTES)) || (rc = ensure(ctx, ctx->hdr_meta, n * 4)))
+            return rc;
+        bdf::PrehdrArgs pa;
+        pa.in = in; pa.in_off = in_off; pa.rows = (uint32_t *)ctx->hdr_rows.p; pa.meta = (uint32_t *)ctx->hdr_meta.p;
+        pa.n = (uint32_t)n;
+        const unsigned long long want = (n + bdf::PREHDR_THREADS - 1) / bdf::PREHDR_THREADS;
+        const unsigned long long cap = (unsigned long long)ctx->sm_count * 32;
+        const unsigned grid = (unsigned)(want < cap ? want : cap);
+        switch (format) {
+            case BDF_RAW: bdf::inflate_prehdr_kernel<BDF_RAW><<<grid, bdf::PREHDR_THREADS, 0, s>>>(pa); break;
+            case BDF_ZLIB: bdf::inflate_prehdr_kernel<BDF_ZLIB><<<grid, bdf::PREHDR_THREADS, 0, s>>>(pa); break;
+            default: bdf::inflate_prehdr_kernel<BDF_GZIP><<<grid, bdf::PREHDR_THREADS, 0, s>>>(pa); break;
+        }
+        ctx->launches++;
+        CK(cudaGetLastError());
+        a.hdr_rows = pa.rows;
+        a.hdr_meta = pa.meta;
+    }
     switch (format) {
         case BDF_RAW: rc = launch_inflate<BDF_RAW>(ctx, a, s, classes); break;
         case BDF_ZLIB: rc = launch_inflate<BDF_ZLIB>(ctx, a, s, classes); break;

@@ -355,6 +355,19 @@ __device__ __forceinline__ void hcs_stage_input(HcsSmem &sm, const HcsStream &st
 // entries of strictly increasing length per position in lists[position * HCS_NLIST ..] (global), the
 // match list the near-optimal parser relaxes (find_matches, src/compress/matchfinder.rs:1283-1296).
 constexpr uint32_t HCS_NLIST = 8;
+// Quick reject of a candidate once a match of `best` bytes is known: a longer match has to agree on the
+// bytes best-3 .. best, so the walk compares that WORD (for best == 3 it is the 4-byte head itself)
+// instead of the single byte at best the reference looks at (matchfinder.rs:829-836).  Same result —
+// only candidates that cannot improve are dropped — and about half as many reach the compare, whose
+// divergent path is what the walk pays for (profiles/r2_hcs_mixed_summary.md).  BDF_HCS_TAIL4=0: the byte test.
+#ifndef BDF_HCS_TAIL4
+#define BDF_HCS_TAIL4 1
+#endif
+#if BDF_HCS_TAIL4
+#define HCS_TAIL_AT(q) hcs_ld32(sm.in, (q) - 3u)
+#else
+#define HCS_TAIL_AT(q) ((uint32_t)sm.in[(q)])
+#endif
 template <bool LISTS>
 __device__ __forceinline__ void hcs_search(HcsSmem &sm, uint32_t len, const HcParams &prm, uint32_t entry, uint32_t nsearch,
                                            uint32_t *lists)
@@ -413,7 +426,7 @@ __device__ __forceinline__ void hcs_search(HcsSmem &sm, uint32_t len, const HcPa
                 for (int burst = 0; burst < HCS_BURST; burst++) {
                     const uint32_t off = p - cur;
                     if (off > 32768u) { done = true; break; }
-                    if (!(best >= 3 && sm.in[cur + best] != tb)) {
+                    if (!(best >= 3 && HCS_TAIL_AT(cur + best) != tb)) {
                         const uint32_t m4 = hcs_ld32(sm.in, cur);
                         const bool eq3 = ((m4 ^ src4) & 0xFFFFFFu) == 0;
                         if (can4) {
@@ -425,13 +438,13 @@ __device__ __forceinline__ void hcs_search(HcsSmem &sm, uint32_t len, const HcPa
                                     // nice_len / 258 reached, or nothing longer can follow (the reference
                                     // leaves its loop at the next candidate: pos + best_len >= len)
                                     if (l >= prm.nice_len || l == 258 || p + l >= len) { done = true; break; }
-                                    tb = sm.in[p + l];
+                                    tb = HCS_TAIL_AT(p + l);
                                 }
                             } else if (best < 3 && eq3) {
                                 best = 3; boff = off;
                                 if (LISTS) { lists[(size_t)p * HCS_NLIST] = 3u | off << 16; nl = 1; }
                                 if (p + 3 >= len) { done = true; break; }
-                                tb = sm.in[p + 3];
+                                tb = HCS_TAIL_AT(p + 3);
                             }
                         } else if (eq3 && best < 3) {          // room == 3: p + 3 == len
                             best = 3; boff = off;

@@ -31,6 +31,12 @@ constexpr int LT_BITS = 9;    // litlen direct-table bits
 constexpr int OT_BITS = 7;    // offset direct-table bits (the precode table, 7 bits, overlays it)
 constexpr int PT_BITS = 7;    // precode direct-table bits
 
+// First-block headers decoded ahead of the inflate kernels (inflate_prehdr.cuh): per stream a row
+// of code lengths and a meta word: [15:0] bits of DEFLATE data up to the end of the header,
+// [20:16] nlit - 257, [25:21] noff - 1, [26] final-block bit, [31] valid.
+constexpr int PREHDR_ROW_BYTES = 320, PREHDR_ROW_WORDS = PREHDR_ROW_BYTES / 4;
+constexpr uint32_t PREHDR_VALID = 1u << 31;
+
 // Table entry (u16 — 32-bit entries cost 1.3 KiB more shared memory per stream, i.e. two CTAs per
 // SM): [3:0] codeword bits (0 = longer than the table), [5:4] kind, [6] literal,
 // [15:7] literal byte / length slot / offset slot / precode symbol.  Base value and extra-bit
@@ -111,6 +117,14 @@ struct BitReader {
         left = 32 - 8 * (int32_t)mis;
         widx = 1;
         ahead = load_word(1);
+    }
+    // the stream without loading anything: seek_bits() / seek() start the reader
+    __device__ __forceinline__ void attach(const uint8_t *ptr, uint32_t n)
+    {
+        p = ptr; len = n;
+        mis = (uint32_t)(reinterpret_cast<uintptr_t>(ptr) & 3u);
+        nwords = (mis + n + 3) >> 2;
+        buf = 0; left = 0; widx = 0; ahead = 0;
     }
     // keep at least 33 valid bits
     __device__ __forceinline__ void refill()
@@ -912,12 +926,11 @@ __device__ __forceinline__ int decode_step(const Grp<G> &g, BitReader &br, OutSt
 template <class SM> __device__ __forceinline__ uint16_t *precode_table(SM &sm) { return sm.off_tab; }
 
 template <int G, class SM, int LTB = LT_BITS, int OTB = OT_BITS>
-__device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, SM &sm, uint32_t &nlong)
+__device__ int read_code_lengths(const Grp<G> &g, BitReader &br, SM &sm, unsigned &nlit, unsigned &noff)
 {
-    nlong = 1;
     br.refill();
-    const unsigned nlit = 257 + br.take(5);
-    const unsigned noff = 1 + br.take(5);
+    nlit = 257 + br.take(5);
+    noff = 1 + br.take(5);
     const unsigned npre = 4 + br.take(4);
     uint8_t *pre_lens = sm.lens + 300;   // only needed until the precode table is built
     {
@@ -984,6 +997,29 @@ __device__ int read_dynamic_header(const Grp<G> &g, BitReader &br, SM &sm, uint3
     }
     if (br.overrun()) return BDF_SHORT_INPUT;
     g.sync();
+    return BDF_OK;
+}
+
+// The same lengths from the row the pre-pass left (inflate_prehdr.cuh); the reader restarts behind
+// the header.
+template <int G, class SM>
+__device__ __forceinline__ void load_code_lengths(const Grp<G> &g, BitReader &br, SM &sm, uint32_t meta, const uint32_t *row,
+                                                  unsigned &nlit, unsigned &noff)
+{
+    nlit = 257 + ((meta >> 16) & 31u);
+    noff = 1 + ((meta >> 21) & 31u);
+    uint32_t *lw = reinterpret_cast<uint32_t *>(sm.lens);
+    const unsigned nw = (nlit + noff + 3) >> 2;
+    for (unsigned j = g.lane; j < nw; j += G) lw[j] = __ldg(row + j);
+    br.seek_bits((int64_t)(meta & 0xFFFFu));
+    g.sync();
+}
+
+// decode tables of a dynamic block from the code lengths in sm.lens
+template <int G, class SM, int LTB = LT_BITS, int OTB = OT_BITS>
+__device__ int build_dynamic_codes(const Grp<G> &g, SM &sm, unsigned nlit, unsigned noff, uint32_t &nlong)
+{
+    nlong = 1;
     uint32_t long_off = 0, long_lit = 0;
     if (!build_code<CODE_OFFSET, OTB, G>(g, sm.lens + nlit, noff, sm.off_tab, sm.off_sorted, sm.off_code, sm.bs, &long_off))
         return BDF_BAD_DATA;
@@ -1007,25 +1043,36 @@ __device__ void load_static_codes(const Grp<G> &g, SM &sm)
 // Called by ALL lanes of the warp together; `have` says whether this group has a stream.  Both
 // loops run until no group of the warp has work left (a group that is done idles), so the groups
 // meet again at every block header and at every decoding step.
+// hdr_meta / hdr_rows + idx: the stream's first header as the pre-pass left it (inflate_prehdr.cuh).  A reader
+// that was attached instead of started (widx == 0) marks a stream whose first header comes from there, so
+// the state costs no register once the first block is under way.
 template <bool ADLER, int G>
 __device__ int inflate_stream(const Grp<G> &g, const uint8_t *p, uint32_t len, OutState &o, InflateSmem<G> &sm,
-                              uint32_t *used, bool have)
+                              uint32_t *used, bool have, const uint32_t *hdr_meta, const uint32_t *hdr_rows,
+                              unsigned long long idx)
 {
     BitReader br;
-    br.p = p; br.len = 0; br.mis = 0; br.nwords = 0; br.widx = 0; br.ahead = 0; br.buf = 0; br.left = 0;
-    if (have) br.init(p, len);
+    br.p = p; br.len = 0; br.mis = 0; br.nwords = 0; br.widx = 1; br.ahead = 0; br.buf = 0; br.left = 0;
+    if (have) {
+        if (hdr_meta && (__ldg(hdr_meta + idx) & PREHDR_VALID)) br.attach(p, len);
+        else br.init(p, len);
+    }
     int st = BDF_OK;
     bool live = have;
     while (__any_sync(BDF_FULL_MASK, live)) {
         bool inblock = false;
         unsigned final = 0;
-        if (live) {
+        const bool pre = live && br.widx == 0;
+        if (live && !pre) {
             br.refill();
             if (br.consumed_bits() + 3 > (int64_t)len * 8) { st = BDF_SHORT_INPUT; live = false; }
         }
         if (live) {
-            final = br.take(1);
-            const unsigned type = br.take(2);
+            unsigned type = 2;
+            if (!pre) {
+                final = br.take(1);
+                type = br.take(2);
+            }
             if (type == 0) {
                 // stored block (src/decompress/mod.rs:282-346, x86.rs:2216-2246)
                 uint32_t at = (uint32_t)((br.consumed_bits() + 7) >> 3);
@@ -1060,7 +1107,13 @@ __device__ int inflate_stream(const Grp<G> &g, const uint8_t *p, uint32_t len, O
                 if (type == 1) {
                     load_static_codes<G>(g, sm);
                 } else {
-                    st = read_dynamic_header<G>(g, br, sm, nlong);
+                    unsigned nlit = 0, noff = 0;
+                    if (pre) {
+                        const uint32_t meta = __ldg(hdr_meta + idx);
+                        final = (meta >> 26) & 1u;
+                        load_code_lengths<G>(g, br, sm, meta, hdr_rows + idx * PREHDR_ROW_WORDS, nlit, noff);
+                    } else st = read_code_lengths<G>(g, br, sm, nlit, noff);
+                    if (st == BDF_OK) st = build_dynamic_codes<G>(g, sm, nlit, noff, nlong);
                     if (st != BDF_OK) live = false;
                 }
                 // A block without codewords longer than the direct tables never looks at the sorted
@@ -1156,6 +1209,9 @@ struct InflateArgs {
     unsigned long long *work_counter2;   // queue head of inflate_lane_kernel
     uint8_t *lane_scratch;               // inflate_lane_kernel: LANE_SORTED_BYTES per lane of the grid
     uint32_t n;
+    // first-block headers decoded by inflate_prehdr_kernel (null: the kernels read every header themselves)
+    const uint32_t *hdr_rows;            // n x PREHDR_ROW_WORDS
+    const uint32_t *hdr_meta;            // n
     // Two engines share a batch: a stream whose capacity is at least split_ratio times its
     // compressed length ("heavy": a few long matches, run-length / periodic data) goes to the
     // lane-group kernel, every other stream to the lane-per-stream kernel (inflate_lane.cuh).
@@ -1214,7 +1270,8 @@ inflate_kernel(InflateArgs a)
     __shared__ uint32_t s_x2n[32];
     InflateSmem<G> &sm = reinterpret_cast<InflateSmem<G> *>(smem_raw)[threadIdx.x / G];
     static_assert(offsetof(InflateSmem<G>, bs) % 16 == 0 && offsetof(InflateSmem<G>, lit_sorted) % 16 == 0 &&
-                      sizeof(InflateSmem<G>) % 16 == 0 && BLOCK_BUF_SCRATCH<G> >= 1024 && sizeof(sm.lens) == 328,
+                      sizeof(InflateSmem<G>) % 16 == 0 && BLOCK_BUF_SCRATCH<G> >= 1024 && sizeof(sm.lens) == 328 &&
+                      offsetof(InflateSmem<G>, lens) % 4 == 0,
                   "builder scratch + lens (and the long-code lists in front of them) double as the 16-byte "
                   "aligned block buffer of copy_match");
     const Grp<G> g;
@@ -1279,7 +1336,7 @@ inflate_kernel(InflateArgs a)
         else st = inflate_frame_header<FORMAT>(p, len, at, dlen);
         const bool go = st == BDF_OK;
         // all lanes of the warp call this together (see inflate_stream)
-        const int ist = inflate_stream<FORMAT == BDF_ZLIB, G>(g, p + at, dlen, o, sm, &used, go);
+        const int ist = inflate_stream<FORMAT == BDF_ZLIB, G>(g, p + at, dlen, o, sm, &used, go, a.hdr_meta, a.hdr_rows, idx);
         if (go) {
             st = ist;
             if (st == BDF_OK && FORMAT == BDF_ZLIB) {

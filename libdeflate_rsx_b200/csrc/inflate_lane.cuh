@@ -28,7 +28,7 @@
 //    symbol (up to two literals, or a length/offset pair) | copy up to 8 bytes of the pending
 //    match | flush one sector.
 //  * Block headers are read by the whole warp for one stream at a time with the lane-group
-//    kernel's code (read_dynamic_header / build_code with G = 32): the owner's bit reader is
+//    kernel's code (read_code_lengths / build_code with G = 32): the owner's bit reader is
 //    broadcast, the tables are built into the owner's slot, the reader is handed back.
 #pragma once
 #include "inflate.cuh"
@@ -54,7 +54,7 @@ struct LaneSmem {                   // one per warp
     BuildScratch<32> bs;
     uint8_t lens[328];
 };
-// what read_dynamic_header / load_static_codes see (member names of InflateSmem)
+// what read_code_lengths / build_dynamic_codes / load_static_codes see (member names of InflateSmem)
 struct LaneView {
     uint16_t *lit_tab, *off_tab, *lit_sorted, *off_sorted;
     HuffCode &lit_code, &off_code;
@@ -154,6 +154,8 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
     constexpr bool ADLER = FORMAT == BDF_ZLIB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LaneSmem<LTB, OTB> &sm = *reinterpret_cast<LaneSmem<LTB, OTB> *>(smem_raw);
+    using LaneSmemT = LaneSmem<LTB, OTB>;
+    static_assert(offsetof(LaneSmemT, lens) % 4 == 0, "load_code_lengths stores words");
     const unsigned lane = threadIdx.x;
     const Grp<32> g;
     LaneTab<LTB, OTB> &T = sm.tab[lane];
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
     uint32_t sumA = 0;
     uint64_t sumB = 0;
     uint32_t idx = 0;
+    uint32_t pre_meta = 0;           // first header of the stream as the pre-pass left it (inflate_prehdr.cuh), 0 = none
     int st = LS_NEW, status = BDF_OK;
     bool q_empty = false;
 
@@ -281,8 +284,13 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                             at = 0;
                             if (len64 > 0xFFFFFFF0ull) status = BDF_BAD_DATA;    // outside this engine's range
                             else status = inflate_frame_header<FORMAT>(sp, (uint32_t)len64, at, dlen);
-                            if (status == BDF_OK) { br.init(sp + at, dlen); st = LS_HDR; }
-                            else st = LS_END;
+                            pre_meta = 0;
+                            if (status == BDF_OK) {
+                                if (a.hdr_meta) pre_meta = __ldg(a.hdr_meta + my);
+                                if (pre_meta & PREHDR_VALID) br.attach(sp + at, dlen);
+                                else br.init(sp + at, dlen);
+                                st = LS_HDR;
+                            } else st = LS_END;
                         }
                     }
                 }
@@ -294,6 +302,8 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                 const unsigned s = __ffs(hdr) - 1;
                 hdr &= hdr - 1;
                 BitReader b = bcast_reader(br, s);
+                uint32_t pm = __shfl_sync(BDF_FULL_MASK, pre_meta, s);
+                const uint32_t *prow = a.hdr_rows + (size_t)__shfl_sync(BDF_FULL_MASK, idx, s) * PREHDR_ROW_WORDS;
                 int hst = BDF_OK;           // status that ends the stream (uniform)
                 bool ended = false, fin = false;
                 LaneTab<LTB, OTB> &Ts = sm.tab[s];
@@ -301,17 +311,24 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                     a.lane_scratch + ((size_t)blockIdx.x * 32 + s) * LANE_SORTED_BYTES);
                 LaneView v{Ts.lit_tab, Ts.off_tab, sorted_s, sorted_s + 288, sm.lit_code, sm.off_code, sm.bs, sm.lens};
                 for (;;) {                  // stored blocks are consumed here, one after the other
-                    b.refill();
-                    if (b.consumed_bits() + 3 > (int64_t)b.len * 8) { hst = BDF_SHORT_INPUT; ended = true; break; }
-                    fin = b.take(1) != 0;
-                    const unsigned type = b.take(2);
+                    unsigned type = 2;
+                    if (pm & PREHDR_VALID) fin = (pm >> 26 & 1u) != 0;
+                    else {
+                        b.refill();
+                        if (b.consumed_bits() + 3 > (int64_t)b.len * 8) { hst = BDF_SHORT_INPUT; ended = true; break; }
+                        fin = b.take(1) != 0;
+                        type = b.take(2);
+                    }
                     if (type == 1) {
                         load_static_codes<32, LaneView, LTB, OTB>(g, v);
                         break;
                     }
                     if (type == 2) {
                         uint32_t nlong;
-                        hst = read_dynamic_header<32, LaneView, LTB, OTB>(g, b, v, nlong);
+                        unsigned nlit = 0, noff = 0;
+                        if (pm & PREHDR_VALID) load_code_lengths<32, LaneView>(g, b, v, pm, prow, nlit, noff);
+                        else hst = read_code_lengths<32, LaneView, LTB, OTB>(g, b, v, nlit, noff);
+                        if (hst == BDF_OK) hst = build_dynamic_codes<32, LaneView, LTB, OTB>(g, v, nlit, noff, nlong);
                         if (hst != BDF_OK) ended = true;
                         break;
                     }
@@ -361,6 +378,7 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                 __syncwarp();               // tables and code descriptions of slot s were written by all lanes
                 if (lane == s) {
                     br = b;
+                    pre_meta = 0;
                     final_blk = fin;
                     if (ended) { status = hst; st = LS_END; }
                     else {
