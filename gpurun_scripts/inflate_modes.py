@@ -20,6 +20,9 @@ ENV = {"group": {"BDF_INFLATE_MODE": "group"}, "lane0": {"BDF_INFLATE_MODE": "la
        # the same without the first-block header pre-pass (inflate_prehdr.cuh)
        "auto_nopre": {"BDF_INFLATE_MODE": "auto", "BDF_INFLATE_PREHDR": "0"},
        "group_nopre": {"BDF_INFLATE_MODE": "group", "BDF_INFLATE_PREHDR": "0"},
+       "serial1": {"BDF_INFLATE_MODE": "auto", "BDF_INFLATE_SERIAL": "1"},
+       "serial2": {"BDF_INFLATE_MODE": "auto", "BDF_INFLATE_SERIAL": "2"},
+       "concurrent": {"BDF_INFLATE_MODE": "auto", "BDF_INFLATE_SERIAL": "0"},
        "lane0_nopre": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "0", "BDF_INFLATE_PREHDR": "0"}}
 dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(dev)
@@ -31,7 +34,7 @@ KINDS = {
 }
 ctxs = {}
 for m in want:
-    for k in ("BDF_INFLATE_MODE", "BDF_LANE_CFG", "BDF_INFLATE_PREHDR"):
+    for k in ("BDF_INFLATE_MODE", "BDF_LANE_CFG", "BDF_INFLATE_PREHDR", "BDF_INFLATE_SERIAL"):
         os.environ.pop(k, None)
     os.environ.update(ENV[m])
     ctxs[m] = b.Context(0)

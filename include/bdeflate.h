@@ -196,6 +196,51 @@ int bdf_compress_size_batch_device(bdf_ctx *ctx, int level, const uint8_t *in, c
 int bdf_compress_size_batch_host(bdf_ctx *ctx, int level, const uint8_t *in, const uint64_t *in_off,
                                  size_t n, int final_block, uint64_t *out_size, int32_t *status);
 
+/*
+ * Decompressor::decompress_streaming(input, window, &mut write_pos) -> (result, in_consumed,
+ * out_produced) for many decoders at once (src/decompress/mod.rs:204-372) — the call
+ * DeflateDecoder::read makes whenever its window runs dry (src/stream.rs:263-376).  Raw DEFLATE.
+ *
+ * Decoder i continues where its state stands: it reads in[in_off[i] .. in_off[i+1]) — the bytes the
+ * caller holds that the decoder has not consumed yet — and appends to its window
+ * window[win_off[i] .. win_off[i] + win_cap[i]) at win_pos[i].  The bytes below win_pos[i] are the
+ * output so far (match history: the caller keeps at least the last 32768 bytes there);
+ * win_cap[i] must be at least 32768 + 258.  On return win_pos[i] has advanced by what was produced,
+ * in_consumed[i] is the number of input bytes used up (drop them before the next call) and
+ * status[i] says why the step stopped:
+ *   BDF_OK                  the final block has ended (the state stays "done");
+ *   BDF_SHORT_INPUT         more input is needed.  A decoder asks for up to 570 bytes in front of a
+ *                           dynamic block header; set in_final[i] != 0 once no more input exists —
+ *                           then BDF_SHORT_INPUT means the stream is truncated;
+ *   BDF_INSUFFICIENT_SPACE  fewer than 258 bytes of room left: drain / shift the window;
+ *   BDF_BAD_DATA            invalid stream (sticky).
+ * A zeroed bdf_inflate_state is the start of a stream.  The state is plain data (368 bytes): it can
+ * be stored, copied or moved between calls and ctxs.  Output bytes do not depend on how the input
+ * and the window were cut.
+ * Engine: one lane per decoder state (csrc/inflate_resume.cuh) — built for MANY concurrent
+ * decoders, not for the speed of a single one.
+ */
+typedef struct bdf_inflate_state {
+    uint32_t phase;       /* 0 block header next, 1 stored block body, 2 Huffman block body, 3 done, 4 failed */
+    uint32_t final_block; /* BFINAL of the current block */
+    uint32_t bit_off;     /* bits of the next input byte already consumed (0..7) */
+    uint32_t stored_rem;  /* bytes left in a stored block */
+    uint32_t nlit, noff;  /* code counts of the current Huffman block */
+    uint32_t reserved[2];
+    uint64_t total_in, total_out;
+    uint8_t lens[320];    /* code lengths of the current Huffman block */
+} bdf_inflate_state;
+int bdf_inflate_resume_batch_device(bdf_ctx *ctx, size_t n, bdf_inflate_state *states, const uint8_t *in,
+                                    const uint64_t *in_off, const uint8_t *in_final, uint8_t *window,
+                                    const uint64_t *win_off, const uint64_t *win_cap, uint64_t *win_pos,
+                                    uint64_t *in_consumed, int32_t *status, void *stream);
+/* host pointers; only window bytes [old win_pos, new win_pos) are written back, and the history the
+ * step can refer to (the 32768 bytes below win_pos) is what goes to the device */
+int bdf_inflate_resume_batch_host(bdf_ctx *ctx, size_t n, bdf_inflate_state *states, const uint8_t *in,
+                                  const uint64_t *in_off, const uint8_t *in_final, uint8_t *window,
+                                  const uint64_t *win_off, const uint64_t *win_cap, uint64_t *win_pos,
+                                  uint64_t *in_consumed, int32_t *status);
+
 /* adler32(1, data) / crc32(0, data) per stream (src/adler32/mod.rs:114-152,
  * src/crc32/mod.rs:331-365). */
 int bdf_checksum_batch_device(bdf_ctx *ctx, int kind, const uint8_t *in,

@@ -24,6 +24,7 @@ EXPORTS = [
     "bdf_checksum_batch_host", "bdf_gather_streams_device", "bdf_compress_units_host",
     "bdf_compress_size_batch_device", "bdf_compress_size_batch_host",
     "bdf_compress_batch_host_dense", "bdf_compress_batch_host_sg", "bdf_debug_check_failures",
+    "bdf_inflate_resume_batch_device", "bdf_inflate_resume_batch_host",
 ]
 
 
@@ -80,6 +81,10 @@ def load():
     L.bdf_compress_size_batch_device.argtypes = [vp, C.c_int, vp, vp, sz, C.c_int, vp, vp, vp]
     L.bdf_compress_size_batch_host.restype = C.c_int
     L.bdf_compress_size_batch_host.argtypes = [vp, C.c_int, vp, vp, sz, C.c_int, vp, vp]
+    L.bdf_inflate_resume_batch_device.restype = C.c_int
+    L.bdf_inflate_resume_batch_device.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.bdf_inflate_resume_batch_host.restype = C.c_int
+    L.bdf_inflate_resume_batch_host.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.bdf_gather_streams_device.restype = C.c_int
     L.bdf_gather_streams_device.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
     return L

@@ -20,6 +20,7 @@
 #include "inflate.cuh"
 #include "inflate_lane.cuh"
 #include "inflate_prehdr.cuh"
+#include "inflate_resume.cuh"
 #include "deflate.cuh"
 
 namespace {
@@ -63,10 +64,13 @@ struct bdf_ctx {
     int inflate_mode = 0;                       // 0 = both engines, split by expansion ratio; 1 = lane groups only; 2 = lane per stream only (BDF_INFLATE_MODE)
     int inflate_split = 16;                     // expansion ratio from which a stream goes to the lane-group kernel (BDF_INFLATE_SPLIT)
     int lane_cfg = 0;                           // direct-table bits of inflate_lane_kernel: 0 = (8, 7), 7 warps / SM; 1 = (9, 6), 5 warps / SM; 2 = (8, 6), 8 warps / SM (BDF_LANE_CFG)
+    int inflate_serial = 1;                     // the two engines of a call: 1 = lane groups, then lanes, on the caller's stream; 2 = the other order; 0 = side by side on two streams (BDF_INFLATE_SERIAL)
     int inflate_prehdr = 1;                     // first-block headers decoded by inflate_prehdr_kernel ahead of the engines (BDF_INFLATE_PREHDR=0: off)
     int lane_warps_per_sm = 0;                  // cap on resident warps of inflate_lane_kernel, 0 = what fits (BDF_LANE_WARPS)
     bdf::DeflateScratch deflate_scratch;
     DevBuf in, out, in_off, out_off, max_out, out_size, status, checksum, lane_scratch, dense, dense_off, hdr_rows, hdr_meta;
+    DevBuf rs_states, rs_in, rs_meta, rs_final, rs_win, rs_status;      // bdf_inflate_resume_batch_host staging
+    bool resume_attr_set = false;
     void *h_stage[2] = {nullptr, nullptr};      // pinned: packing buffers of a scattered input
     size_t h_stage_cap[2] = {0, 0};
     void *h_result = nullptr;                   // pinned: dense result on its way to bound-spaced slots
@@ -197,9 +201,9 @@ int launch_inflate_group(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s
     }
 }
 
-// Both engines of a decompress call: the lane-group kernel on the caller's stream, the
-// lane-per-stream kernel beside it on the ctx's aux stream (fork / join with events), each
-// taking the streams of its class.  classes: bit 0 = heavy streams present, bit 1 = light ones
+// Both engines of a decompress call, each taking the streams of its class: one after the other on
+// the caller's stream (default), or side by side — the lane-per-stream kernel on the ctx's aux
+// stream, fork / join with events.  classes: bit 0 = heavy streams present, bit 1 = light ones
 // (3 when the caller cannot tell, i.e. the offsets live on the device).
 template <int FORMAT>
 int launch_inflate(bdf_ctx *ctx, bdf::InflateArgs a, cudaStream_t s, int classes)
@@ -209,6 +213,17 @@ int launch_inflate(bdf_ctx *ctx, bdf::InflateArgs a, cudaStream_t s, int classes
     a.split_ratio = (uint32_t)ctx->inflate_split;
     if (classes == 1) return launch_inflate_group<FORMAT>(ctx, a, s);
     if (classes == 2) return launch_inflate_lane<FORMAT>(ctx, a, s);
+    if (ctx->inflate_serial) {
+        // One after the other on the caller's stream.  Side by side (two streams, fork / join) was the
+        // first design; measured with 65536 x 64 KiB streams per call it is never better and often much
+        // worse — text 105 vs 140 GB/s, binary 64 vs 84, mixed 79 vs 86 (gpurun_out/inflate_modes_r3c.txt):
+        // whichever kernel becomes resident first keeps shared memory the other one's CTAs need, and the
+        // lane-per-stream kernel lives on its occupancy.  The heavy streams take a few percent of a
+        // call's time at most (4.9 TB/s against ~0.1), so nothing is lost by running them first.
+        int rc = ctx->inflate_serial == 1 ? launch_inflate_group<FORMAT>(ctx, a, s) : launch_inflate_lane<FORMAT>(ctx, a, s);
+        if (rc) return rc;
+        return ctx->inflate_serial == 1 ? launch_inflate_lane<FORMAT>(ctx, a, s) : launch_inflate_group<FORMAT>(ctx, a, s);
+    }
     CK(cudaEventRecord(ctx->ev_fork, s));
     CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
     int rc = launch_inflate_lane<FORMAT>(ctx, a, ctx->aux_stream);
@@ -266,6 +281,7 @@ int bdf_ctx_create(int device, bdf_ctx **out)
     }
     if (const char *e = getenv("BDF_LANE_CFG")) ctx->lane_cfg = atoi(e) >= 0 && atoi(e) <= 2 ? atoi(e) : 0;
     if (const char *e = getenv("BDF_INFLATE_PREHDR")) ctx->inflate_prehdr = atoi(e) != 0;
+    if (const char *e = getenv("BDF_INFLATE_SERIAL")) ctx->inflate_serial = atoi(e);
     if (const char *e = getenv("BDF_LANE_WARPS")) ctx->lane_warps_per_sm = atoi(e) > 0 ? atoi(e) : 0;
     {
         // Device-to-host result copies per call: eight concurrent copies (56.6 vs 51 GB/s for one when a
@@ -311,7 +327,7 @@ void bdf_ctx_destroy(bdf_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->in, &ctx->out, &ctx->in_off, &ctx->out_off, &ctx->max_out,
-                      &ctx->out_size, &ctx->status, &ctx->checksum, &ctx->lane_scratch, &ctx->dense, &ctx->dense_off, &ctx->hdr_rows, &ctx->hdr_meta, &ctx->u_in_off, &ctx->u_tmp_off,
+                      &ctx->out_size, &ctx->status, &ctx->checksum, &ctx->lane_scratch, &ctx->dense, &ctx->dense_off, &ctx->hdr_rows, &ctx->hdr_meta, &ctx->rs_states, &ctx->rs_in, &ctx->rs_meta, &ctx->rs_final, &ctx->rs_win, &ctx->rs_status, &ctx->u_in_off, &ctx->u_tmp_off,
                       &ctx->u_size, &ctx->u_status, &ctx->u_flags, &ctx->u_begin, &ctx->u_tmp};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -508,6 +524,110 @@ int bdf_decompress_batch_device(bdf_ctx *ctx, int format, const uint8_t *in, con
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     return decompress_device_locked(ctx, format, in, in_off, n, out, out_off, max_out, out_size, checksum,
                                     status, s);
+}
+
+// ------------------------------------------------------- resumable decoding
+static int resume_device_locked(bdf_ctx *ctx, size_t n, bdf_inflate_state *states, const uint8_t *in,
+                                const uint64_t *in_off, const uint8_t *in_final, uint8_t *window,
+                                const uint64_t *win_off, const uint64_t *win_cap, uint64_t *win_pos,
+                                uint64_t *in_consumed, int32_t *status, cudaStream_t s)
+{
+    if (n > 0xFFFFFFF0ull) return fail(ctx, BDF_E_ARG, "too many decoder states");
+    if (!ctx->resume_attr_set) {
+        CK(cudaFuncSetAttribute(bdf::inflate_resume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bdf::RESUME_SMEM));
+        ctx->resume_attr_set = true;
+    }
+    bdf::ResumeArgs a;
+    a.states = states; a.in = in; a.in_off = in_off; a.in_final = in_final; a.window = window;
+    a.win_off = win_off; a.win_cap = win_cap; a.win_pos = win_pos; a.in_consumed = in_consumed; a.status = status;
+    a.n = (uint32_t)n;
+    const unsigned grid = (unsigned)((n + bdf::RESUME_THREADS - 1) / bdf::RESUME_THREADS);
+    bdf::inflate_resume_kernel<<<grid, bdf::RESUME_THREADS, bdf::RESUME_SMEM, s>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return BDF_E_OK;
+}
+
+int bdf_inflate_resume_batch_device(bdf_ctx *ctx, size_t n, bdf_inflate_state *states, const uint8_t *in,
+                                    const uint64_t *in_off, const uint8_t *in_final, uint8_t *window,
+                                    const uint64_t *win_off, const uint64_t *win_cap, uint64_t *win_pos,
+                                    uint64_t *in_consumed, int32_t *status, void *stream)
+{
+    if (!ctx) return BDF_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (n == 0) return BDF_E_OK;
+    if (!states || !in || !in_off || !in_final || !window || !win_off || !win_cap || !win_pos || !in_consumed || !status)
+        return fail(ctx, BDF_E_ARG, "null pointer");
+    CK(cudaSetDevice(ctx->device));
+    return resume_device_locked(ctx, n, states, in, in_off, in_final, window, win_off, win_cap, win_pos, in_consumed,
+                                status, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int bdf_inflate_resume_batch_host(bdf_ctx *ctx, size_t n, bdf_inflate_state *states, const uint8_t *in,
+                                  const uint64_t *in_off, const uint8_t *in_final, uint8_t *window,
+                                  const uint64_t *win_off, const uint64_t *win_cap, uint64_t *win_pos,
+                                  uint64_t *in_consumed, int32_t *status)
+{
+    if (!ctx) return BDF_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (n == 0) return BDF_E_OK;
+    if (!states || !in || !in_off || !in_final || !window || !win_off || !win_cap || !win_pos || !in_consumed || !status)
+        return fail(ctx, BDF_E_ARG, "null pointer");
+    constexpr uint64_t HISTORY = 32768;
+    size_t win_bytes = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (in_off[i] > in_off[i + 1]) return fail(ctx, BDF_E_ARG, "in_off is not ascending");
+        const uint64_t e = win_off[i] + win_cap[i];
+        if (e < win_off[i] || e > BDF_MAX_SLAB_BYTES) return fail(ctx, BDF_E_ARG, "win_off + win_cap overflows");
+        if (win_pos[i] > win_cap[i]) return fail(ctx, BDF_E_ARG, "win_pos beyond win_cap");
+        if (e > win_bytes) win_bytes = (size_t)e;
+    }
+    if (in_off[n] > BDF_MAX_SLAB_BYTES) return fail(ctx, BDF_E_ARG, "input too large");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t in_bytes = (size_t)in_off[n];
+    int rc;
+    // rs_meta: in_off (n + 1) | win_off | win_cap | win_pos | in_consumed   (u64 each)
+    if ((rc = ensure(ctx, ctx->rs_states, n * sizeof(bdf_inflate_state))) || (rc = ensure(ctx, ctx->rs_in, in_bytes + 8)) ||
+        (rc = ensure(ctx, ctx->rs_meta, (5 * n + 1) * 8)) || (rc = ensure(ctx, ctx->rs_final, n)) ||
+        (rc = ensure(ctx, ctx->rs_win, win_bytes + 8)) || (rc = ensure(ctx, ctx->rs_status, n * 4)))
+        return rc;
+    uint64_t *m = (uint64_t *)ctx->rs_meta.p;
+    uint64_t *d_in_off = m, *d_win_off = m + (n + 1), *d_win_cap = d_win_off + n, *d_win_pos = d_win_cap + n, *d_used = d_win_pos + n;
+    CK(cudaMemcpyAsync(ctx->rs_states.p, states, n * sizeof(bdf_inflate_state), cudaMemcpyHostToDevice, s));
+    if (in_bytes) CK(cudaMemcpyAsync(ctx->rs_in.p, in, in_bytes, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_in_off, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_win_off, win_off, n * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_win_cap, win_cap, n * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_win_pos, win_pos, n * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->rs_final.p, in_final, n, cudaMemcpyHostToDevice, s));
+    // the history a step can refer to: the 32 KiB below the write position
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t hist = win_pos[i] < HISTORY ? win_pos[i] : HISTORY;
+        const uint64_t at = win_off[i] + win_pos[i] - hist;
+        if (hist) CK(cudaMemcpyAsync((uint8_t *)ctx->rs_win.p + at, window + at, (size_t)hist, cudaMemcpyHostToDevice, s));
+    }
+    std::vector<uint64_t> old_pos(win_pos, win_pos + n);
+    rc = resume_device_locked(ctx, n, (bdf_inflate_state *)ctx->rs_states.p, (const uint8_t *)ctx->rs_in.p, d_in_off,
+                              (const uint8_t *)ctx->rs_final.p, (uint8_t *)ctx->rs_win.p, d_win_off, d_win_cap, d_win_pos,
+                              d_used, (int32_t *)ctx->rs_status.p, s);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(states, ctx->rs_states.p, n * sizeof(bdf_inflate_state), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(win_pos, d_win_pos, n * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(in_consumed, d_used, n * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(status, ctx->rs_status.p, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    bool any = false;
+    for (size_t i = 0; i < n; i++) {
+        if (win_pos[i] < old_pos[i] || win_pos[i] > win_cap[i]) return fail(ctx, BDF_E_CUDA, "resume step returned an invalid window position");
+        const uint64_t at = win_off[i] + old_pos[i], cnt = win_pos[i] - old_pos[i];
+        if (cnt) {
+            CK(cudaMemcpyAsync(window + at, (const uint8_t *)ctx->rs_win.p + at, (size_t)cnt, cudaMemcpyDeviceToHost, s));
+            any = true;
+        }
+    }
+    if (any) CK(cudaStreamSynchronize(s));
+    return BDF_E_OK;
 }
 
 // Copies [beg, end) of a device slab to the same offsets of a host buffer.  Large ranges go out as

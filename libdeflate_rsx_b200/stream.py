@@ -8,11 +8,10 @@ chunks of the buffer — and ends in a sync flush, except the last chunk of
 therefore byte-identical to the reference encoder's for the same sequence of
 writes / flushes.
 
-`DeflateDecoder` gives the same `read` interface (stream.rs:263-376) but is not
-incremental: the reference keeps a 64 KiB window and resumes the decoder state
-between reads; the batch engine inflates whole streams, so the first read
-drains the inner reader and inflates everything (growing the output room on
-BDF_INSUFFICIENT_SPACE up to DEFLATE's maximum expansion).
+`DeflateDecoder` is the incremental reader of stream.rs:243-376: a 64 KiB window,
+input pulled from the inner reader on demand, the decoder resumed where the
+last read left it (`bdf_inflate_resume_batch_host`: Decompressor::decompress_streaming
+for many decoder states per launch).
 """
 import numpy as np
 
@@ -108,37 +107,142 @@ class DeflateEncoder:
         return False
 
 
-class DeflateDecoder:
-    def __init__(self, inner, context=None):
-        self.inner = inner
-        self.ctx = context or default_context()
-        self._out = None
-        self._pos = 0
+STATE_BYTES = 368          # sizeof(bdf_inflate_state), include/bdeflate.h
+PH_START, PH_STORED, PH_HUFF, PH_DONE, PH_FAILED = range(5)
 
-    def _inflate_all(self):
-        from .batch import BatchDecompressor
-        data = self.inner.read()
-        d = BatchDecompressor(format=N.RAW, context=self.ctx)
-        flat = np.frombuffer(data or b"\0", dtype=np.uint8)
-        off = np.array([0, len(data)], dtype=np.uint64)
-        cap = max(4 * len(data), 1 << 16)
-        limit = 1032 * len(data) + (1 << 16)           # DEFLATE cannot expand further
-        while True:
-            out, out_off, out_size, status = d.decompress_flat(flat, off, np.array([cap], dtype=np.uint64))
-            if status[0] == N.OK:
-                return out[:int(out_size[0])].tobytes()
-            if status[0] != N.INSUFFICIENT_SPACE or cap >= limit:
-                raise OSError("Decompression failed")        # io::ErrorKind::InvalidData, stream.rs:330-340
-            cap = min(cap * 4, limit)
+
+def resume_step_batch(states, inputs, finals, windows, write_pos, context=None):
+    """bdf_inflate_resume_batch_host for n decoders: Decompressor::decompress_streaming
+    (src/decompress/mod.rs:204-372) as a batch.  states: list of writable 368-byte buffers (updated in
+    place); inputs: list of bytes-like; finals: list of bool; windows: list of C-contiguous np.uint8
+    arrays (written in place from write_pos[i] on).  -> list of (status, consumed, new write_pos)."""
+    ctx = context or default_context()
+    n = len(states)
+    if n == 0:
+        return []
+    st = np.frombuffer(b"".join(bytes(x) for x in states), dtype=np.uint8).copy()
+    lens = np.array([len(x) for x in inputs], dtype=np.uint64)
+    in_off = np.zeros(n + 1, dtype=np.uint64)
+    in_off[1:] = np.cumsum(lens)
+    flat = np.frombuffer(b"".join(bytes(x) for x in inputs) or b"\0", dtype=np.uint8)
+    fin = np.array([1 if f else 0 for f in finals], dtype=np.uint8)
+    caps = np.array([w.size for w in windows], dtype=np.uint64)
+    win_off = np.zeros(n, dtype=np.uint64)
+    win_off[1:] = np.cumsum(caps)[:-1]
+    win = np.concatenate(windows) if n > 1 else windows[0]
+    pos = np.array(write_pos, dtype=np.uint64)
+    used = np.zeros(n, dtype=np.uint64)
+    status = np.zeros(n, dtype=np.int32)
+    ctx.check(ctx._lib.bdf_inflate_resume_batch_host(ctx.handle, n, _ptr(st), _ptr(flat), _ptr(in_off), _ptr(fin),
+                                                     _ptr(win), _ptr(win_off), _ptr(caps), _ptr(pos), _ptr(used),
+                                                     _ptr(status)))
+    out = []
+    for i in range(n):
+        states[i][:] = st[i * STATE_BYTES:(i + 1) * STATE_BYTES].tobytes()
+        if n > 1:
+            a, b = int(write_pos[i]), int(pos[i])
+            windows[i][a:b] = win[int(win_off[i]) + a:int(win_off[i]) + b]
+        out.append((int(status[i]), int(used[i]), int(pos[i])))
+    return out
+
+
+class UnexpectedEof(OSError, EOFError):
+    """io::ErrorKind::UnexpectedEof"""
+
+
+class DeflateDecoder:
+    """DeflateDecoder<R: Read> (src/stream.rs:243-376): an incremental reader over a raw DEFLATE stream.
+
+    Like the reference it keeps a 64 KiB window whose lower half is match history, pulls input from
+    the inner reader only when the decoder asks for it, and resumes the decoder where the last read
+    left it — here through bdf_inflate_resume_batch_host with one decoder state (the engine advances
+    many states per launch; a pool of decoders would batch their steps, see resume_step_batch).
+    Differences from the reference's loop follow from the engine's stop rules (include/bdeflate.h): a
+    step stops when fewer than 258 bytes of room are left (not exactly 0), so the window is 64 KiB +
+    258 bytes and shifts at that point; and the decoder asks for up to 570 bytes in front of a
+    dynamic header, so end of input is passed down as `in_final`.
+    Errors: OSError("deflate decompression failed") for invalid data (io::ErrorKind::InvalidData,
+    stream.rs:330-340), UnexpectedEof (an OSError and an EOFError) for a truncated stream (:353-366).
+    """
+
+    HISTORY = 32 * 1024
+    WINDOW = 64 * 1024 + 258
+    INPUT_CHUNK = 32 * 1024
+
+    def __init__(self, inner, context=None, _step=None):
+        self.inner = inner
+        self.ctx = context
+        self._step = _step                   # tests: the host build of the same decoder core
+        self.state = bytearray(STATE_BYTES)  # zeroed = start of a stream
+        self.window = np.zeros(self.WINDOW, dtype=np.uint8)
+        self.read_pos = 0
+        self.write_pos = 0
+        self.input = bytearray()
+        self.in_final = False
+        self.done = False
+        self.steps = 0
+
+    def _phase(self):
+        return int.from_bytes(self.state[0:4], "little")
+
+    def _one_step(self):
+        self.steps += 1
+        if self._step is not None:
+            return self._step(self.state, bytes(self.input), self.in_final, self.window, self.write_pos)
+        return resume_step_batch([self.state], [bytes(self.input)], [self.in_final], [self.window],
+                                 [self.write_pos], self.ctx or default_context())[0]
+
+    def _fill(self):
+        """Decodes until the window holds unread bytes or the stream is over (the loop of stream.rs:283-375)."""
+        while self.read_pos == self.write_pos and not self.done:
+            if self.WINDOW - self.write_pos < 258 and self.write_pos > self.HISTORY:
+                # everything has been read: keep the last 32 KiB as history (stream.rs:284-295)
+                shift = self.write_pos - self.HISTORY
+                self.window[:self.HISTORY] = self.window[shift:self.write_pos].copy()
+                self.write_pos = self.HISTORY
+                self.read_pos = self.HISTORY
+            status, used, new_pos = self._one_step()
+            del self.input[:used]
+            self.write_pos = new_pos
+            if status == N.OK:
+                self.done = True
+                break
+            if status == N.BAD_DATA:
+                raise OSError("deflate decompression failed")
+            if self.write_pos > self.read_pos or status == N.INSUFFICIENT_SPACE:
+                continue
+            # BDF_SHORT_INPUT without progress: more input, or the end of it
+            if self.in_final:
+                raise UnexpectedEof("unexpected EOF")
+            chunk = self.inner.read(self.INPUT_CHUNK)
+            if chunk:
+                self.input += chunk
+            elif not self.input and self._phase() == PH_START:
+                self.done = True             # the input ends between two blocks: Ok(0), stream.rs:367-369
+            else:
+                self.in_final = True
 
     def read(self, n=-1):
-        if self._out is None:
-            self._out = self._inflate_all()
+        """Up to n bytes (at least one unless the stream is over); n < 0: everything that is left."""
         if n is None or n < 0:
-            n = len(self._out) - self._pos
-        chunk = self._out[self._pos:self._pos + n]
-        self._pos += len(chunk)
+            return self.read_to_end()
+        if n == 0:
+            return b""
+        self._fill()
+        count = min(n, self.write_pos - self.read_pos)
+        chunk = self.window[self.read_pos:self.read_pos + count].tobytes()
+        self.read_pos += count
         return chunk
 
+    def readinto(self, buf):
+        chunk = self.read(len(buf))
+        buf[:len(chunk)] = chunk
+        return len(chunk)
+
     def read_to_end(self):
-        return self.read(-1)
+        parts = []
+        while True:
+            chunk = self.read(self.WINDOW)
+            if not chunk:
+                return b"".join(parts)
+            parts.append(chunk)
