@@ -134,7 +134,7 @@ int bdf_decompress_batch_host(bdf_ctx *ctx, int format, const uint8_t *in,
  * its bytes.
  * The *_device call cannot see the lengths without synchronising: it runs the 64 KiB instances
  * and sets status[i] = BDF_STREAM_UNSUPPORTED for a longer stream (level 0 takes any length up
- * to 256 KiB there).
+ * to 256 KiB there); bdf_compress_batch_device_any is the device-pointer call for any length.
  */
 int bdf_compress_batch_device(bdf_ctx *ctx, int level, int format,
                               const uint8_t *in, const uint64_t *in_off, size_t n,
@@ -144,6 +144,15 @@ int bdf_compress_batch_host(bdf_ctx *ctx, int level, int format, const uint8_t *
                             const uint64_t *in_off, size_t n, uint8_t *out,
                             const uint64_t *out_off, uint64_t *out_size,
                             int32_t *status);
+/* Device pointers, any stream length (Compressor::compress takes any length,
+ * src/compress/mod.rs:699-772): like bdf_compress_batch_device, but the call first reads the
+ * offsets back (8 (n + 1) bytes, one synchronisation of `stream`) to choose the kernel instances and
+ * size the slab of the 256 KiB units; the data never leaves the device and the call returns with
+ * the work enqueued.  Same bytes as the *_host call. */
+int bdf_compress_batch_device_any(bdf_ctx *ctx, int level, int format,
+                                  const uint8_t *in, const uint64_t *in_off, size_t n,
+                                  uint8_t *out, const uint64_t *out_off,
+                                  uint64_t *out_size, int32_t *status, void *stream);
 
 /*
  * The same call with the result packed: stream i is out[out_off[i] .. out_off[i+1]) (out_off has

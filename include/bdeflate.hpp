@@ -7,7 +7,7 @@
 //       a stream that fails yields std::nullopt                                     (:95-96)
 //       result length = min(inputs, max_out_sizes)  (zip, :79-81)
 // plus the `format` selector of the C ABI, the safe API of src/api.rs (Compressor / Decompressor)
-// and the stream encoder of src/stream.rs (DeflateEncoder).  Header-only; link with libbdeflate.so.
+// and the stream adapters of src/stream.rs (DeflateEncoder, DeflateDecoder).  Header-only; link with libbdeflate.so.
 // A call-level failure (no GPU, CUDA error, unsupported request) throws — there
 // is no CPU fallback behind this API.
 #pragma once
@@ -272,6 +272,82 @@ private:
     size_t buffer_size_ = 1024 * 1024;
     Bytes buffer_;
     std::shared_ptr<Context> ctx_;
+};
+
+// ---------------------------------------------------------------------------------------------
+// DeflateDecoder of the reference (src/stream.rs:243-376): an incremental reader over a raw DEFLATE
+// stream.  A 64 KiB window whose lower half is match history, input pulled from `Source` only when
+// the decoder asks for it, the decoder resumed where the last read left it through
+// bdf_inflate_resume_batch_host (one decoder state here; the call advances many per launch).
+// `Source` needs size_t read(uint8_t *, size_t) returning 0 at the end of input.
+// Errors: std::runtime_error("deflate decompression failed") (InvalidData, :330-340) and
+// std::runtime_error("unexpected EOF") (:353-366).
+template <class Source>
+class DeflateDecoder {
+public:
+    explicit DeflateDecoder(Source &src, std::shared_ptr<Context> ctx = nullptr)
+        : src_(&src), ctx_(ctx ? ctx : std::make_shared<Context>()), window_(WINDOW)
+    {
+        std::memset(&state_, 0, sizeof(state_));
+    }
+    // up to n bytes, 0 only at the end of the stream
+    size_t read(uint8_t *buf, size_t n)
+    {
+        if (n == 0) return 0;
+        fill();
+        const size_t count = std::min<size_t>(n, write_pos_ - read_pos_);
+        std::memcpy(buf, window_.data() + read_pos_, count);
+        read_pos_ += count;
+        return count;
+    }
+    Bytes read_to_end()
+    {
+        Bytes out, piece(WINDOW);
+        for (;;) {
+            const size_t k = read(piece.data(), piece.size());
+            if (k == 0) return out;
+            out.insert(out.end(), piece.begin(), piece.begin() + k);
+        }
+    }
+
+private:
+    static constexpr size_t HISTORY = 32 * 1024, WINDOW = 64 * 1024 + 258, INPUT_CHUNK = 32 * 1024;
+    void fill()
+    {
+        while (read_pos_ == write_pos_ && !done_) {
+            if (WINDOW - write_pos_ < 258 && write_pos_ > HISTORY) {     // everything was read: keep the history (:284-295)
+                std::memmove(window_.data(), window_.data() + (write_pos_ - HISTORY), HISTORY);
+                write_pos_ = read_pos_ = HISTORY;
+            }
+            const uint8_t dummy = 0;
+            const uint64_t in_off[2] = {0, input_.size()}, win_off = 0, win_cap = WINDOW;
+            const uint8_t fin = in_final_ ? 1 : 0;
+            uint64_t pos = write_pos_, used = 0;
+            int32_t status = 0;
+            ctx_->check(bdf_inflate_resume_batch_host(ctx_->get(), 1, &state_, input_.empty() ? &dummy : input_.data(), in_off,
+                                                      &fin, window_.data(), &win_off, &win_cap, &pos, &used, &status));
+            input_.erase(input_.begin(), input_.begin() + (size_t)used);
+            write_pos_ = (size_t)pos;
+            if (status == BDF_OK) { done_ = true; break; }
+            if (status == BDF_BAD_DATA) throw std::runtime_error("deflate decompression failed");
+            if (write_pos_ > read_pos_ || status == BDF_INSUFFICIENT_SPACE) continue;
+            if (in_final_) throw std::runtime_error("unexpected EOF");
+            const size_t have = input_.size();
+            input_.resize(have + INPUT_CHUNK);
+            const size_t got = src_->read(input_.data() + have, INPUT_CHUNK);
+            input_.resize(have + got);
+            if (got == 0) {
+                if (input_.empty() && state_.phase == 0) done_ = true;      // the input ends between two blocks: Ok(0), :367-369
+                else in_final_ = true;
+            }
+        }
+    }
+    Source *src_;
+    std::shared_ptr<Context> ctx_;
+    bdf_inflate_state state_;
+    Bytes window_, input_;
+    size_t read_pos_ = 0, write_pos_ = 0;
+    bool in_final_ = false, done_ = false;
 };
 
 }  // namespace bdf

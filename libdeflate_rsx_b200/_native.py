@@ -24,7 +24,7 @@ EXPORTS = [
     "bdf_checksum_batch_host", "bdf_gather_streams_device", "bdf_compress_units_host",
     "bdf_compress_size_batch_device", "bdf_compress_size_batch_host",
     "bdf_compress_batch_host_dense", "bdf_compress_batch_host_sg", "bdf_debug_check_failures",
-    "bdf_inflate_resume_batch_device", "bdf_inflate_resume_batch_host",
+    "bdf_inflate_resume_batch_device", "bdf_inflate_resume_batch_host", "bdf_compress_batch_device_any",
 ]
 
 
@@ -65,6 +65,8 @@ def load():
     L.bdf_decompress_batch_host.argtypes = [vp, C.c_int, vp, vp, sz, vp, vp, vp, vp, vp, vp]
     L.bdf_compress_batch_device.restype = C.c_int
     L.bdf_compress_batch_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, sz, vp, vp, vp, vp, vp]
+    L.bdf_compress_batch_device_any.restype = C.c_int
+    L.bdf_compress_batch_device_any.argtypes = [vp, C.c_int, C.c_int, vp, vp, sz, vp, vp, vp, vp, vp]
     L.bdf_compress_batch_host.restype = C.c_int
     L.bdf_compress_batch_host.argtypes = [vp, C.c_int, C.c_int, vp, vp, sz, vp, vp, vp, vp]
     L.bdf_compress_batch_host_dense.restype = C.c_int

@@ -755,8 +755,19 @@ int bdf_compress_batch_device(bdf_ctx *ctx, int level, int format, const uint8_t
 // Streams above 64 KiB: units of at most 256 KiB (Compressor::compress, src/compress/mod.rs:699-772)
 // through the 256 KiB kernel instances into a temporary slab, then deflate_join_kernel.  Called with
 // the inputs already on the device and the ctx mutex held.
+// Device buffers of a batch (flat input + offsets, bound-spaced output slab + per-stream results).
+struct DevBatch {
+    const uint8_t *in;
+    const uint64_t *in_off;
+    uint8_t *out;
+    const uint64_t *out_off;
+    uint64_t *out_size;
+    int32_t *status;
+};
+
+// in_off: host copy of the offsets; d: where the batch lives on the device
 static int compress_chunked_locked(bdf_ctx *ctx, int level, int format, const uint64_t *in_off, size_t n,
-                                   cudaStream_t s)
+                                   cudaStream_t s, const DevBatch &d)
 {
     constexpr uint64_t CHUNK = 256 * 1024;
     std::vector<uint64_t> uoff, toff;
@@ -795,25 +806,57 @@ static int compress_chunked_locked(bdf_ctx *ctx, int level, int format, const ui
     CK(cudaStreamSynchronize(s));              // the vectors above die with this frame
     CK(cudaEventRecord(ctx->ev0, s));
     bdf::DeflateArgs a;
-    a.in = (const uint8_t *)ctx->in.p; a.in_off = (const uint64_t *)ctx->u_in_off.p;
+    a.in = d.in; a.in_off = (const uint64_t *)ctx->u_in_off.p;
     a.out = (uint8_t *)ctx->u_tmp.p; a.out_off = (const uint64_t *)ctx->u_tmp_off.p;
     a.out_size = (uint64_t *)ctx->u_size.p; a.status = (int32_t *)ctx->u_status.p;
     a.n = (uint32_t)nu; a.level = level > 12 ? 12 : level; a.format = BDF_RAW;
     a.unit_flags = (const uint8_t *)ctx->u_flags.p;
     if ((rc = run_deflate(ctx, a, s, max_unit))) return rc;
     bdf::JoinArgs j;
-    j.in = (const uint8_t *)ctx->in.p; j.in_off = (const uint64_t *)ctx->in_off.p;
+    j.in = d.in; j.in_off = d.in_off;
     j.unit_begin = (const uint32_t *)ctx->u_begin.p; j.tmp = (const uint8_t *)ctx->u_tmp.p;
     j.tmp_off = (const uint64_t *)ctx->u_tmp_off.p; j.unit_size = (const uint64_t *)ctx->u_size.p;
-    j.unit_status = (const int32_t *)ctx->u_status.p; j.out = (uint8_t *)ctx->out.p;
-    j.out_off = (const uint64_t *)ctx->out_off.p; j.out_size = (uint64_t *)ctx->out_size.p;
-    j.status = (int32_t *)ctx->status.p; j.n = (uint32_t)n; j.level = a.level; j.format = format;
+    j.unit_status = (const int32_t *)ctx->u_status.p; j.out = d.out;
+    j.out_off = d.out_off; j.out_size = d.out_size;
+    j.status = d.status; j.n = (uint32_t)n; j.level = a.level; j.format = format;
     unsigned long long want = (n + bdf::JOIN_WARPS - 1) / bdf::JOIN_WARPS;
     unsigned long long full = (unsigned long long)ctx->sm_count * 16;
     bdf::deflate_join_kernel<<<(unsigned)(want < full ? want : full), bdf::JOIN_WARPS * 32, 0, s>>>(j);
     ctx->launches++;
     CK(cudaGetLastError());
     return BDF_E_OK;
+}
+
+// Any stream length on device-resident data.  The kernels to run (64 KiB instances, or 256 KiB units +
+// join) and the size of the unit slab depend on the lengths, so the offsets are read back once
+// (8 (n + 1) bytes and one synchronisation of `stream`); everything else stays on the device and the
+// call returns with the work enqueued, like bdf_compress_batch_device.
+int bdf_compress_batch_device_any(bdf_ctx *ctx, int level, int format, const uint8_t *in, const uint64_t *in_off,
+                                  size_t n, uint8_t *out, const uint64_t *out_off, uint64_t *out_size,
+                                  int32_t *status, void *stream)
+{
+    if (!ctx) return BDF_E_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (bad_format(format)) return fail(ctx, BDF_E_ARG, "unknown format");
+    if (level < 0) return fail(ctx, BDF_E_ARG, "negative level");
+    if (n == 0) return BDF_E_OK;
+    if (!in || !in_off || !out || !out_off || !out_size || !status) return fail(ctx, BDF_E_ARG, "null pointer");
+    if (n > 0xFFFFFFF0ull) return fail(ctx, BDF_E_ARG, "too many streams");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    std::vector<uint64_t> h_off(n + 1);
+    CK(cudaMemcpyAsync(h_off.data(), in_off, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    uint64_t max_len = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (h_off[i] > h_off[i + 1]) return fail(ctx, BDF_E_ARG, "in_off is not ascending");
+        if (h_off[i + 1] - h_off[i] > max_len) max_len = h_off[i + 1] - h_off[i];
+    }
+    if (h_off[n] > BDF_MAX_SLAB_BYTES) return fail(ctx, BDF_E_ARG, "input too large");
+    if (max_len <= (level == 0 ? 256u * 1024u : 65536u))
+        return compress_device_locked(ctx, level, format, in, in_off, n, out, out_off, out_size, status, s);
+    const DevBatch d{in, in_off, out, out_off, out_size, status};
+    return compress_chunked_locked(ctx, level, format, h_off.data(), n, s, d);
 }
 
 // ---- host compress calls.  One implementation behind three entry points (flat input + bound-spaced
@@ -968,7 +1011,9 @@ static int compress_host_impl(bdf_ctx *ctx, int level, int format, const HostInp
         }
     }
     if (chunked) {
-        rc = compress_chunked_locked(ctx, level, format, in_off, n, s);
+        const DevBatch d{(const uint8_t *)ctx->in.p, (const uint64_t *)ctx->in_off.p, (uint8_t *)ctx->out.p,
+                         (const uint64_t *)ctx->out_off.p, (uint64_t *)ctx->out_size.p, (int32_t *)ctx->status.p};
+        rc = compress_chunked_locked(ctx, level, format, in_off, n, s, d);
         if (rc) return rc;
     }
     CK(cudaEventRecord(ctx->ev1, s));

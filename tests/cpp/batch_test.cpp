@@ -135,6 +135,34 @@ int main()
         bdf::BatchDecompressor d(BDF_RAW, ctx);
         auto out = d.decompress_batch({{sink.data.data(), sink.data.size()}}, {data.size()});
         CHECK(out[0].has_value() && *out[0] == data);
+        // stream decoder: tests/stream_test.rs:41-54 reads the encoder's output back in small pieces
+        struct VecSource {
+            const std::vector<uint8_t> *v;
+            size_t pos = 0, piece;
+            size_t read(uint8_t *p, size_t n)
+            {
+                const size_t k = std::min({n, piece, v->size() - pos});
+                std::memcpy(p, v->data() + pos, k);
+                pos += k;
+                return k;
+            }
+        };
+        VecSource src{&sink.data, 0, 5000};
+        bdf::DeflateDecoder<VecSource> dec(src, ctx);
+        std::vector<uint8_t> back, piece(1000);
+        for (;;) {
+            const size_t k = dec.read(piece.data(), piece.size());
+            if (k == 0) break;
+            back.insert(back.end(), piece.begin(), piece.begin() + k);
+        }
+        CHECK(back == data);
+        // a truncated stream is an error, not a short result
+        std::vector<uint8_t> cut(sink.data.begin(), sink.data.begin() + sink.data.size() / 2);
+        VecSource src2{&cut, 0, 70000};
+        bdf::DeflateDecoder<VecSource> dec2(src2, ctx);
+        bool threw = false;
+        try { dec2.read_to_end(); } catch (const std::runtime_error &) { threw = true; }
+        CHECK(threw);
     }
     // size estimation (Compressor::compress_to_size, src/compress/mod.rs:1073-1094): at the greedy /
     // lazy levels the estimate is the length of the stream the compressor writes
