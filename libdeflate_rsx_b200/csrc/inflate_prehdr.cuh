@@ -32,27 +32,36 @@ struct PrehdrArgs {
     uint32_t n;
 };
 
-// One stream's first header.  ptab: this warp's precode tables, entry i of lane l at ptab[i * 32 + l]
-// (sym << 3 | codeword bits); row: this lane's 320-byte row in shared memory.  Returns the meta
-// word, 0 if the header is left to the inflate kernels.
-__device__ __forceinline__ uint32_t prehdr_decode(const uint8_t *p, uint32_t dlen, uint8_t *ptab, uint32_t *row, unsigned lane)
+// ---- a dynamic block header read by ONE lane, in two pieces so that a lane can also spread the
+// work over the rounds of its own decode loop (inflate_lane.cuh):
+//   lane_hdr_begin    block bits, counts, precode lengths -> the lane's precode table
+//   lane_hdr_lengths  up to `budget` code-length symbols of the run-length coded litlen + offset
+//                     lengths (:441-497) into the lane's row
+// ptab: 128 entries (sym << 3 | codeword bits), entry i at ptab[i * pstride]; row: bytes, any address
+// space.  Every anomaly (not a dynamic block, short input, a precode that is not a complete code,
+// "repeat previous" at position 0) is reported as failure WITHOUT a verdict: the caller hands the
+// header to the group-wide reader, which applies the reference's accept / reject rules.
+struct LaneHdr {
+    uint32_t nlit, noff, final;
+    uint32_t i, prev;            // progress of the run-length decode
+};
+
+__device__ __forceinline__ bool lane_hdr_begin(BitReader &br, uint32_t dlen, uint8_t *ptab, unsigned pstride, LaneHdr &h)
 {
-    BitReader br;
-    br.init(p, dlen);
     br.refill();
-    if (br.consumed_bits() + 3 > (int64_t)dlen * 8) return 0;
-    const unsigned final = br.take(1);
-    if (br.take(2) != 2) return 0;
+    if (br.consumed_bits() + 3 > (int64_t)dlen * 8) return false;
+    h.final = br.take(1);
+    if (br.take(2) != 2) return false;
     br.refill();
-    const unsigned nlit = 257 + br.take(5);
-    const unsigned noff = 1 + br.take(5);
+    h.nlit = 257 + br.take(5);
+    h.noff = 1 + br.take(5);
     const unsigned npre = 4 + br.take(4);
     br.refill();
     const unsigned n_lo = npre < 10 ? npre : 10;
     const uint32_t lo = br.take(3 * n_lo);
     br.refill();
     const uint32_t hi = npre > 10 ? br.take(3 * (npre - 10)) : 0;
-    if (br.overrun()) return 0;
+    if (br.overrun()) return false;
     // precode lengths by symbol, 3 bits each (order 16,17,18,0,8,7,9,6,10,5,11,4,12,3,13,2,14,1,15)
     const uint64_t perm_lo = 16ull | 17ull << 5 | 18ull << 10 | 0ull << 15 | 8ull << 20 | 7ull << 25 |
                              9ull << 30 | 6ull << 35 | 10ull << 40 | 5ull << 45;
@@ -81,7 +90,7 @@ __device__ __forceinline__ uint32_t prehdr_decode(const uint8_t *p, uint32_t dle
             code = (code + c) << 1;
         }
     }
-    if (kraft != 128u) return 0;
+    if (kraft != 128u) return false;
 #pragma unroll 1
     for (unsigned s = 0; s < 19; s++) {
         const unsigned l = (unsigned)(pl >> (3 * s)) & 7u;
@@ -90,22 +99,35 @@ __device__ __forceinline__ uint32_t prehdr_decode(const uint8_t *p, uint32_t dle
         next += 1ull << (8 * l);
         const unsigned rev = __brev(code) >> (32 - l);
         const uint8_t e = (uint8_t)(s << 3 | l);
-        for (unsigned i = rev; i < 128; i += 1u << l) ptab[i * 32 + lane] = e;
+        for (unsigned i = rev; i < 128; i += 1u << l) ptab[i * pstride] = e;
     }
-    // run-length decode of the litlen + offset code lengths (:441-497); overruns of a repeat are clamped
-    uint8_t *rowb = reinterpret_cast<uint8_t *>(row);
-    const unsigned total = nlit + noff;
-    unsigned i = 0, prev = 0;
+    h.i = 0; h.prev = 0;
+    return true;
+}
+
+// -> 1 all lengths decoded (the caller still checks br.overrun()), 0 budget used up, -1 failure
+struct PlainRefill {
+    __device__ __forceinline__ void operator()(BitReader &b) const { b.refill(); }
+};
+template <class Refill = PlainRefill>
+__device__ __forceinline__ int lane_hdr_lengths(BitReader &br, const uint8_t *ptab, unsigned pstride, uint8_t *rowb, LaneHdr &h,
+                                                unsigned budget, Refill refill = Refill())
+{
+    const unsigned total = h.nlit + h.noff;
+    unsigned i = h.i, prev = h.prev;
+    int done = 0;
 #pragma unroll 1
     while (i < total) {
-        br.refill();                       // >= 33 valid bits: two plain lengths, or one and a repeat symbol
-        uint32_t e = ptab[br.peek(7) * 32 + lane];
+        if (budget == 0) goto out;
+        budget--;
+        refill(br);                        // >= 33 valid bits: two plain lengths, or one and a repeat symbol
+        uint32_t e = ptab[br.peek(7) * pstride];
         if ((e >> 3) < 16) {
             rowb[i++] = (uint8_t)(e >> 3);
             prev = e >> 3;
             br.drop(e & 7u);
             if (i >= total) break;
-            e = ptab[br.peek(7) * 32 + lane];
+            e = ptab[br.peek(7) * pstride];
             if ((e >> 3) < 16) {
                 rowb[i++] = (uint8_t)(e >> 3);
                 prev = e >> 3;
@@ -117,7 +139,7 @@ __device__ __forceinline__ uint32_t prehdr_decode(const uint8_t *p, uint32_t dle
         const unsigned sym = e >> 3;
         unsigned rep, val;
         if (sym == 16) {
-            if (i == 0) return 0;
+            if (i == 0) { done = -1; goto out; }
             rep = 3 + br.take(2);
             val = prev;
         } else if (sym == 17) {
@@ -127,16 +149,33 @@ __device__ __forceinline__ uint32_t prehdr_decode(const uint8_t *p, uint32_t dle
             rep = 11 + br.take(7);
             val = 0;
         }
-        if (rep > total - i) rep = total - i;
+        if (rep > total - i) rep = total - i;           // overruns of a repeat are clamped (:462-493)
         for (unsigned q = 0; q < rep; q++) rowb[i + q] = (uint8_t)val;
         prev = val;
         i += rep;
     }
+    done = 1;
+out:
+    h.i = i; h.prev = prev;
+    return done;
+}
+
+// One stream's first header.  ptab: this warp's precode tables, entry i of lane l at ptab[i * 32 + l];
+// row: this lane's 320-byte row in shared memory.  Returns the meta word, 0 if the header is left to
+// the inflate kernels.
+__device__ __forceinline__ uint32_t prehdr_decode(const uint8_t *p, uint32_t dlen, uint8_t *ptab, uint32_t *row, unsigned lane)
+{
+    BitReader br;
+    br.init(p, dlen);
+    LaneHdr h;
+    if (!lane_hdr_begin(br, dlen, ptab + lane, 32, h)) return 0;
+    uint8_t *rowb = reinterpret_cast<uint8_t *>(row);
+    if (lane_hdr_lengths(br, ptab + lane, 32, rowb, h, ~0u) != 1) return 0;
     if (br.overrun()) return 0;
-    for (unsigned q = total; q < (unsigned)PREHDR_ROW_BYTES; q++) rowb[q] = 0;
+    for (unsigned q = h.nlit + h.noff; q < (unsigned)PREHDR_ROW_BYTES; q++) rowb[q] = 0;
     const int64_t cb = br.consumed_bits();
     if (cb < 0 || cb > 0xFFFF) return 0;
-    return PREHDR_VALID | (uint32_t)cb | (nlit - 257) << 16 | (noff - 1) << 21 | final << 26;
+    return PREHDR_VALID | (uint32_t)cb | (h.nlit - 257) << 16 | (h.noff - 1) << 21 | h.final << 26;
 }
 
 template <int FORMAT>

@@ -29,6 +29,23 @@ constexpr uint32_t PREHDR_VALID = 1u << 31;
 """
 
 WRAPPER = r"""
+// the same header in pieces of `budget` symbols, the way the lane kernel spreads it over its rounds
+extern "C" uint32_t prehdr_host_budget(const uint8_t *p, uint32_t dlen, uint8_t *row320, unsigned budget, uint64_t *end_bit)
+{
+    static uint8_t ptab[128];
+    uint8_t row[324];
+    memset(row, 0xEE, sizeof(row));
+    BitReader br;
+    br.init(p, dlen);
+    LaneHdr h;
+    if (!lane_hdr_begin(br, dlen, ptab, 1, h)) return 0;
+    int r;
+    while ((r = lane_hdr_lengths(br, ptab, 1, row, h, budget)) == 0) {}
+    if (r != 1 || br.overrun()) return 0;
+    memcpy(row320, row, 320);
+    *end_bit = (uint64_t)br.consumed_bits();
+    return PREHDR_VALID | (h.nlit - 257) << 16 | (h.noff - 1) << 21 | h.final << 26;
+}
 extern "C" uint32_t prehdr_host(const uint8_t *p, uint32_t dlen, uint8_t *row320, unsigned lane)
 {
     static uint8_t ptab[128 * 32];
@@ -54,7 +71,13 @@ def build():
     inflate = open(os.path.join(CSRC, "inflate.cuh")).read()
     prehdr = open(os.path.join(CSRC, "inflate_prehdr.cuh")).read()
     reader = _cut(inflate, r"^struct BitReader \{", r"^\};")
-    decode = _cut(prehdr, r"^__device__ __forceinline__ uint32_t prehdr_decode", r"^\}")
+    decode = "\n".join([
+        _cut(prehdr, r"^struct LaneHdr \{", r"^\};"),
+        _cut(prehdr, r"^__device__ __forceinline__ bool lane_hdr_begin", r"^\}"),
+        _cut(prehdr, r"^struct PlainRefill \{", r"^\};"),
+        _cut(prehdr, r"^template <class Refill = PlainRefill>", r"^\}"),
+        _cut(prehdr, r"^__device__ __forceinline__ uint32_t prehdr_decode", r"^\}"),
+    ])
     src = os.path.join(BUILD, "prehdr_host.cpp")
     so = os.path.join(BUILD, "libprehdr_host.so")
     text = PRELUDE + reader + "\n" + decode + "\n" + WRAPPER
@@ -65,6 +88,9 @@ def build():
     lib = ctypes.CDLL(so)
     lib.prehdr_host.restype = ctypes.c_uint32
     lib.prehdr_host.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint]
+    lib.prehdr_host_budget.restype = ctypes.c_uint32
+    lib.prehdr_host_budget.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint,
+                                       ctypes.POINTER(ctypes.c_uint64)]
     return lib
 
 
@@ -79,3 +105,14 @@ def decode(lib, data: bytes, lane=0, misalign=0):
     row = ctypes.create_string_buffer(320)
     m = lib.prehdr_host(p, len(data), row, lane)
     return m, row.raw
+
+
+def decode_budget(lib, data: bytes, budget, misalign=0):
+    """lane_hdr_begin + lane_hdr_lengths in pieces of `budget` symbols -> (meta without the bit count, row, end bit)"""
+    pad = b"\xAA" * 8
+    buf = ctypes.create_string_buffer(pad + b"\x55" * misalign + data + pad, 16 + misalign + len(data))
+    p = ctypes.cast(ctypes.addressof(buf) + 8 + misalign, ctypes.c_char_p)
+    row = ctypes.create_string_buffer(320)
+    end = ctypes.c_uint64(0)
+    m = lib.prehdr_host_budget(p, len(data), row, budget, ctypes.byref(end))
+    return m, row.raw, int(end.value)

@@ -180,3 +180,21 @@ def test_random_bits(lib):
         if d:
             d[0] = (d[0] & ~6) | 4          # block type 2
         check(lib, bytes(d), lane=rnd.randrange(32), misalign=rnd.randrange(4))
+
+
+def test_header_in_pieces(lib):
+    """the lane kernel decodes a later block's header a few symbols per round: same lengths, same end bit"""
+    n = 0
+    for k, s in enumerate(sample_streams()):
+        want = ref_header(s)
+        for budget in (1, 2, 7):
+            meta, row, end = prehdr_host.decode_budget(lib, s, budget, misalign=k % 4)
+            if want is None:
+                assert meta == 0
+                continue
+            lens, bits, nlit, noff, final = want
+            assert meta & VALID and end == bits
+            assert 257 + (meta >> 16 & 31) == nlit and 1 + (meta >> 21 & 31) == noff and (meta >> 26 & 1) == final
+            assert list(row[:nlit + noff]) == lens
+            n += 1
+    assert n >= 100
