@@ -1010,6 +1010,7 @@ __device__ __forceinline__ void load_code_lengths(const Grp<G> &g, BitReader &br
     noff = 1 + ((meta >> 21) & 31u);
     uint32_t *lw = reinterpret_cast<uint32_t *>(sm.lens);
     const unsigned nw = (nlit + noff + 3) >> 2;
+    BDF_ASSERT(nw <= (unsigned)PREHDR_ROW_WORDS && (meta & PREHDR_VALID));
     for (unsigned j = g.lane; j < nw; j += G) lw[j] = __ldg(row + j);
     br.seek_bits((int64_t)(meta & 0xFFFFu));
     g.sync();

@@ -99,6 +99,7 @@ __device__ __forceinline__ bool lane_hdr_begin(BitReader &br, uint32_t dlen, uin
         next += 1ull << (8 * l);
         const unsigned rev = __brev(code) >> (32 - l);
         const uint8_t e = (uint8_t)(s << 3 | l);
+        BDF_ASSERT(rev < (1u << l));
         for (unsigned i = rev; i < 128; i += 1u << l) ptab[i * pstride] = e;
     }
     h.i = 0; h.prev = 0;
@@ -150,6 +151,7 @@ __device__ __forceinline__ int lane_hdr_lengths(BitReader &br, const uint8_t *pt
             val = 0;
         }
         if (rep > total - i) rep = total - i;           // overruns of a repeat are clamped (:462-493)
+        BDF_ASSERT(i + rep <= (unsigned)PREHDR_ROW_BYTES);
         for (unsigned q = 0; q < rep; q++) rowb[i + q] = (uint8_t)val;
         prev = val;
         i += rep;

@@ -21,6 +21,8 @@ PRELUDE = r"""
 #define __device__
 #define __forceinline__ inline
 #define BDF_OK 0
+#include <cassert>
+#define BDF_ASSERT(c) assert(c)
 static inline uint32_t __ldg(const uint32_t *p) { return *p; }
 static inline uint8_t __ldg(const uint8_t *p) { return *p; }
 static inline uint32_t __brev(uint32_t x) { uint32_t r = 0; for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i); return r; }

@@ -17,13 +17,17 @@ VARIANTS = [
     {"BDF_HC_KERNEL": "new", "BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "1"},
     {"BDF_HC_KERNEL": "old", "BDF_HC_CTAS_PER_SM": "3", "BDF_INFLATE_MODE": "group", "BDF_INFLATE_GROUP": "32"},
     {"BDF_INFLATE_MODE": "auto", "BDF_INFLATE_SPLIT": "4", "BDF_LANE_WARPS": "3"},
+    # without the first-block header pre-pass; the two engines side by side / lanes first
+    {"BDF_INFLATE_PREHDR": "0", "BDF_INFLATE_SERIAL": "0"},
+    {"BDF_INFLATE_MODE": "lane", "BDF_INFLATE_PREHDR": "0"},
+    {"BDF_INFLATE_SERIAL": "2", "BDF_INFLATE_SPLIT": "2"},
 ]
 
 
 def run(env):
     e = dict(os.environ)
     for k in ("BDF_HC_KERNEL", "BDF_HC_CTAS_PER_SM", "BDF_INFLATE_MODE", "BDF_INFLATE_GROUP", "BDF_LANE_CFG",
-              "BDF_INFLATE_SPLIT", "BDF_LANE_WARPS"):
+              "BDF_INFLATE_SPLIT", "BDF_LANE_WARPS", "BDF_INFLATE_PREHDR", "BDF_INFLATE_SERIAL"):
         e.pop(k, None)
     e.update(env)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "determinism_helper.py")], cwd=ROOT, env=e,
