@@ -1,6 +1,7 @@
 """Levels 10..12 (near-optimal tier): device-resident throughput per corpus kind and the batch's
 compressed size against the oracle's (tolerance 0.5 %); every distinct stream must inflate."""
 import ctypes as C
+import os
 import sys
 import zlib
 
@@ -21,7 +22,9 @@ D = 16
 GEN = {"text": corpus.text_stream, "mixedB": corpus.corpus_b_stream, "corpusA": lambda k: corpus.corpus_a_stream(k % 16),
        "binary": corpus.binary_stream, "lowent": corpus.lowentropy_stream}
 n = n // D * D
-for kind in ("text", "mixedB", "binary", "lowent", "corpusA"):
+KINDS = os.environ.get("KINDS", "text,mixedB,binary,lowent,corpusA").split(",")
+LEVELS = [int(x) for x in os.environ.get("LEVELS", "10,11,12").split(",")]
+for kind in KINDS:
     plain = [GEN[kind](k) for k in range(D)]
     d_in = torch.from_numpy(np.frombuffer(b"".join(plain), dtype=np.uint8).copy()).to(dev).repeat(n // D)
     d_off = torch.arange(n + 1, dtype=torch.int64, device=dev) * 65536
@@ -30,7 +33,7 @@ for kind in ("text", "mixedB", "binary", "lowent", "corpusA"):
     d_ooff = torch.arange(n, dtype=torch.int64, device=dev) * bound
     d_size = torch.zeros(n, dtype=torch.int64, device=dev)
     d_stat = torch.zeros(n, dtype=torch.int32, device=dev)
-    for lvl in (10, 11, 12):
+    for lvl in LEVELS:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         best = None
         for it in range(2):

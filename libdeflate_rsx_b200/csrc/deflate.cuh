@@ -12,6 +12,7 @@
 #include "deflate_bt.cuh"
 #include "deflate_hc.cuh"
 #include "deflate_hcs.cuh"
+#include "deflate_nos_split.cuh"
 #include "deflate_l1.cuh"
 #include "gather.cuh"
 
@@ -20,7 +21,7 @@ namespace bdf {
 struct DeflateScratch {
     void *p = nullptr;
     size_t cap = 0;
-    bool l1_ready = false, hc_ready = false, hcs_ready = false, nos_ready = false;
+    bool l1_ready = false, hc_ready = false, hcs_ready = false, nos_ready = false, nos_split_ready = false;
 };
 inline void deflate_scratch_free(DeflateScratch &s)
 {
@@ -333,6 +334,53 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
     if (no_old < 0) {
         const char *env = getenv("BDF_NO_KERNEL");
         no_old = env && !strcmp(env, "old") ? 1 : 0;
+    }
+    static int nos_split = -1, nos_wave = 0;
+    if (nos_split < 0) {
+        const char *env = getenv("BDF_NOS_SPLIT");
+        nos_split = env ? (atoi(env) != 0) : 1;
+        const char *wenv = getenv("BDF_NOS_WAVE");
+        nos_wave = wenv && atoi(wenv) > 0 ? atoi(wenv) : 8;          // streams per SM and wave
+    }
+    if (!big && !a.size_only && !no_old && nos_split) {
+        // levels 10..12, streams of at most 64 KiB, three kernels per wave of streams (deflate_nos_split.cuh):
+        // the serial cost pass runs one warp per stream for the whole wave instead of one warp per SM
+        const size_t smem = sizeof(HcsSmem);
+        if (!scratch.nos_split_ready) {
+            *why = "cudaFuncSetAttribute(deflate_nos_search_kernel / deflate_nos_emit_kernel)";
+            e = cudaFuncSetAttribute(deflate_nos_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(deflate_nos_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            scratch.nos_split_ready = true;
+            *why = nullptr;
+        }
+        const unsigned wave_max = (unsigned)sm_count * (unsigned)nos_wave;
+        const unsigned wave = a.n < wave_max ? a.n : wave_max;
+        const size_t need = NOS_SPLIT_PER_STREAM * (size_t)wave;
+        if (scratch.cap < need) {
+            if (scratch.p) cudaFree(scratch.p);
+            scratch.p = nullptr;
+            scratch.cap = 0;
+            *why = "cudaMalloc(deflate scratch)";
+            e = cudaMalloc(&scratch.p, need);
+            if (e != cudaSuccess) return e;
+            scratch.cap = need;
+            *why = nullptr;
+        }
+        a.scratch = scratch.p;
+        a.scratch_stride = NOS_SPLIT_PER_STREAM;
+        *nlaunch = 0;
+        for (unsigned first = 0; first < a.n; first += wave) {
+            NosWave wv;
+            wv.first = first;
+            wv.count = a.n - first < wave ? a.n - first : wave;
+            const unsigned grid = wv.count < (unsigned)sm_count ? wv.count : (unsigned)sm_count;
+            deflate_nos_search_kernel<<<grid, HCS_THREADS, smem, s>>>(a, wv);
+            deflate_nos_cost_kernel<<<(wv.count + NOS_COST_WARPS - 1) / NOS_COST_WARPS, NOS_COST_WARPS * 32, 0, s>>>(a, wv);
+            deflate_nos_emit_kernel<<<grid, HCS_THREADS, smem, s>>>(a, wv);
+            *nlaunch += 3;
+        }
+        return cudaGetLastError();
     }
     if (!big && !a.size_only && !no_old) {
         // levels 10..12, streams of at most 64 KiB: the near-optimal parser on the shared-memory

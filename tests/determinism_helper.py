@@ -18,6 +18,10 @@ for level in (2, 6, 9):
     for fmt in (0, 2):
         got = bdf.BatchCompressor(level, format=fmt).compress_batch(bufs)
         print("compress", level, fmt, hashlib.sha256(b"\0".join(got)).hexdigest())
+# levels 10..12 (one CTA per stream or three kernels per wave, BDF_NOS_SPLIT): the same parse either way
+for level in (10, 12):
+    got = bdf.BatchCompressor(level, format=1).compress_batch(bufs[:24] + bufs[150:166])
+    print("compress", level, 1, hashlib.sha256(b"\0".join(got)).hexdigest())
 for fmt in (0, 1, 2):
     comp = [o.compress(b, 1 + i % 9, fmt) or o.compress(b, 0, fmt) for i, b in enumerate(bufs)]
     comp = [c if c is not None else b"" for c in comp]

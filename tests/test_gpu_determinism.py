@@ -20,14 +20,15 @@ VARIANTS = [
     # without the first-block header pre-pass; the two engines side by side / lanes first
     {"BDF_INFLATE_PREHDR": "0", "BDF_INFLATE_SERIAL": "0"},
     {"BDF_INFLATE_MODE": "lane", "BDF_INFLATE_PREHDR": "0"},
-    {"BDF_INFLATE_SERIAL": "2", "BDF_INFLATE_SPLIT": "2"},
+    {"BDF_INFLATE_SERIAL": "2", "BDF_INFLATE_SPLIT": "2", "BDF_NOS_SPLIT": "0"},
+    {"BDF_NOS_WAVE": "1"},
 ]
 
 
 def run(env):
     e = dict(os.environ)
     for k in ("BDF_HC_KERNEL", "BDF_HC_CTAS_PER_SM", "BDF_INFLATE_MODE", "BDF_INFLATE_GROUP", "BDF_LANE_CFG",
-              "BDF_INFLATE_SPLIT", "BDF_LANE_WARPS", "BDF_INFLATE_PREHDR", "BDF_INFLATE_SERIAL"):
+              "BDF_INFLATE_SPLIT", "BDF_LANE_WARPS", "BDF_INFLATE_PREHDR", "BDF_INFLATE_SERIAL", "BDF_NOS_SPLIT", "BDF_NOS_WAVE"):
         e.pop(k, None)
     e.update(env)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "determinism_helper.py")], cwd=ROOT, env=e,
@@ -38,6 +39,6 @@ def run(env):
 
 def test_same_bytes_whatever_the_kernel_choice():
     base = run(VARIANTS[0])
-    assert len(base) == 9
+    assert len(base) == 11
     for v in VARIANTS[1:]:
         assert run(v) == base, v
