@@ -335,13 +335,20 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
         const char *env = getenv("BDF_NO_KERNEL");
         no_old = env && !strcmp(env, "old") ? 1 : 0;
     }
-    static int nos_split = -1, nos_wave = 0;
+    static int nos_split = -1, nos_wave = 0, nos_depth = 0;
     if (nos_split < 0) {
+        const char *denv = getenv("BDF_NOS_DEPTH");
+        nos_depth = denv && atoi(denv) > 0 ? atoi(denv) : 0;
         const char *env = getenv("BDF_NOS_SPLIT");
         nos_split = env ? (atoi(env) != 0) : 1;
         const char *wenv = getenv("BDF_NOS_WAVE");
-        nos_wave = wenv && atoi(wenv) > 0 ? atoi(wenv) : 8;          // streams per SM and wave
+        // streams per SM and wave.  The cost kernel takes ~18.5 ms per wave whatever the wave holds up to a
+        // few dozen warps per SM (a chain of ~300 dependent instructions per step), so a wave should be as
+        // large as the scratch allows: 2.9 MB per stream, 6 GB for 14 x 148 (gpurun_out/nos_probe_r3m_waves.txt:
+        // corpus A level 12 1.60 / 2.64 / 3.77 GB/s at 4 / 8 / 14)
+        nos_wave = wenv && atoi(wenv) > 0 ? atoi(wenv) : 14;
     }
+    a.nos_depth = nos_depth;
     if (!big && !a.size_only && !no_old && nos_split) {
         // levels 10..12, streams of at most 64 KiB, three kernels per wave of streams (deflate_nos_split.cuh):
         // the serial cost pass runs one warp per stream for the whole wave instead of one warp per SM
@@ -355,16 +362,21 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
             *why = nullptr;
         }
         const unsigned wave_max = (unsigned)sm_count * (unsigned)nos_wave;
-        const unsigned wave = a.n < wave_max ? a.n : wave_max;
-        const size_t need = NOS_SPLIT_PER_STREAM * (size_t)wave;
-        if (scratch.cap < need) {
+        unsigned wave = a.n < wave_max ? a.n : wave_max;
+        if (scratch.cap < NOS_SPLIT_PER_STREAM * (size_t)wave) {
             if (scratch.p) cudaFree(scratch.p);
             scratch.p = nullptr;
             scratch.cap = 0;
             *why = "cudaMalloc(deflate scratch)";
-            e = cudaMalloc(&scratch.p, need);
+            // a smaller wave if the device cannot spare the memory
+            for (;;) {
+                e = cudaMalloc(&scratch.p, NOS_SPLIT_PER_STREAM * (size_t)wave);
+                if (e == cudaSuccess || wave <= (unsigned)sm_count) break;
+                (void)cudaGetLastError();
+                wave = wave / 2 > (unsigned)sm_count ? wave / 2 : (unsigned)sm_count;
+            }
             if (e != cudaSuccess) return e;
-            scratch.cap = need;
+            scratch.cap = NOS_SPLIT_PER_STREAM * (size_t)wave;
             *why = nullptr;
         }
         a.scratch = scratch.p;

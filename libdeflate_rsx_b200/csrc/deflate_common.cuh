@@ -37,6 +37,7 @@ struct DeflateArgs {
     // deflate_classify_kernel; a kernel takes the streams whose class equals `want` (NULL: all).
     const uint8_t *klass = nullptr;
     uint8_t want = 0;
+    int nos_depth = 0;       // levels 10..12: chain depth override for experiments (BDF_NOS_DEPTH), 0 = the level's own
 };
 constexpr unsigned UNIT_FINISH = 1u, UNIT_SYNC = 2u, UNIT_CAP5 = 4u;   // CAP5: 5 more bytes of room (DeflateEncoder, src/stream.rs:66-69)
 __host__ __device__ inline uint64_t unit_cap(uint64_t len, unsigned flags) { return len + (len / 65535 + 1) * 5 + 10 + ((flags & 4u) ? 5 : 0); }

@@ -257,7 +257,10 @@ struct HcsStream {                 // uniform per stream
     }
 };
 
-// phase 1: chains of the whole stream (head + link)
+// phase 1: chains of the whole stream (head + link).  H4: chains of 4-byte hashes (near-optimal tier
+// only; the reference's hash chains — and therefore levels 2..9 — hash 3 bytes).
+__device__ __forceinline__ uint32_t hash4(uint32_t v32) { return (v32 * 0x1E35A7BDu) >> 17; }
+template <bool H4 = false>
 __device__ __forceinline__ void hcs_build_chains(HcsSmem &sm, const HcsStream &st)
 {
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -274,8 +277,8 @@ __device__ __forceinline__ void hcs_build_chains(HcsSmem &sm, const HcsStream &s
         // it; the last two positions of a stream are never inserted
         for (uint32_t k = tid; k < HCS_IBLK; k += HCS_THREADS) {
             const uint32_t p = b0 + k;
-            if (p + 3 <= len) {
-                const uint32_t h = hash3(g32(p) & 0xFFFFFFu);
+            if (p + (H4 ? 4u : 3u) <= len) {
+                const uint32_t h = H4 ? hash4(g32(p)) : hash3(g32(p) & 0xFFFFFFu);
                 sm.ins.hbuf[k] = (uint16_t)h;
                 atomicOr(&sm.ins.cls[h & (HCS_INS_WARPS - 1)][k >> 5], 1u << (k & 31u));
             }
@@ -368,9 +371,13 @@ constexpr uint32_t HCS_NLIST = 8;
 #else
 #define HCS_TAIL_AT(q) ((uint32_t)sm.in[(q)])
 #endif
+// near3 (near-optimal tier): the chains in shared memory are chains of 4-byte hashes; near3[p] is the
+// distance from p to the closest earlier position with the same 3-byte hash (0 = none), tried first,
+// so that 3-byte matches are not lost (the shape of the reference's own near-optimal matchfinder: one
+// bucket of 3-byte hashes in front of the structure that holds the 4-byte ones, matchfinder.rs:1344-1463).
 template <bool LISTS>
 __device__ __forceinline__ void hcs_search(HcsSmem &sm, uint32_t len, const HcParams &prm, uint32_t entry, uint32_t nsearch,
-                                           uint32_t *lists)
+                                           uint32_t *lists, const uint16_t *near3 = nullptr)
 {
     const unsigned lane = threadIdx.x & 31u;
     // ---- search: warps take chunks of 32 positions from a counter; every lane walks one chain at a
@@ -402,7 +409,26 @@ __device__ __forceinline__ void hcs_search(HcsSmem &sm, uint32_t len, const HcPa
                                 *reinterpret_cast<uint4 *>(lists + (size_t)p * HCS_NLIST + k) = make_uint4(0, 0, 0, 0);
                             nl = 0;
                         }
-                        if (p + 3 > len || first == 0) sm.w.res[q] = 0;
+                        if (LISTS && near3) {
+                            best = 0; boff = 0; depth = 0;
+                            src4 = hcs_ld32(sm.in, p);
+                            room = len - p < 258u ? len - p : 258u;
+                            can4 = p + 4 <= len;
+                            bool over = false;                  // nothing can follow the 3-byte candidate
+                            const uint32_t n3 = p + 3 <= len ? (uint32_t)near3[p] : 0u;
+                            if (n3 != 0 && n3 <= 32768u) {
+                                const uint32_t m4 = hcs_ld32(sm.in, p - n3);
+                                if (((m4 ^ src4) & 0xFFFFFFu) == 0) {
+                                    const uint32_t l = (can4 && m4 == src4) ? 4 + hcs_prefix(sm.in, p - n3 + 4, p + 4, room - 4) : 3u;
+                                    best = l; boff = n3;
+                                    lists[(size_t)p * HCS_NLIST] = l | n3 << 16; nl = 1;
+                                    if (l >= prm.nice_len || l == 258 || p + l >= len) over = true;
+                                    else tb = HCS_TAIL_AT(p + l);
+                                }
+                            }
+                            if (over || !can4 || first == 0) sm.w.res[q] = best | boff << 16;
+                            else { cur = p - first; active = true; }
+                        } else if (p + 3 > len || first == 0) sm.w.res[q] = 0;
                         else {
                             cur = p - first; best = 0; boff = 0; depth = 0;
                             src4 = hcs_ld32(sm.in, p);
@@ -924,11 +950,12 @@ __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_hcs_kernel(DeflateArgs
 //     backwards makes the result a step function — exactly what the parallel parse of this file
 //     consumes, so there is no serial backtrack;
 //   * pass 3: that parse over the block (records, final histograms), then the block is encoded.
-constexpr size_t NOS_SCRATCH_PER_CTA = HCS_SCRATCH_PER_CTA + 65536 * sizeof(uint32_t) * 2 + 65536 * HCS_NLIST * sizeof(uint32_t);
+constexpr size_t NOS_SCRATCH_PER_CTA = HCS_SCRATCH_PER_CTA + 65536 * sizeof(uint32_t) * 2 + 65536 * HCS_NLIST * sizeof(uint32_t) +
+                                      65536 * sizeof(uint16_t);        // + near3 (behind the lists)
 constexpr uint32_t NOS_INF = 0x0FFFFFFFu;
 constexpr uint32_t NOS_SHORTER = 7;
 
-__device__ __forceinline__ HcParams nos_params(int level)
+__device__ __forceinline__ HcParams nos_params(int level, int depth_override = 0)
 {
     // depth / nice length of the chain walks.  The reference's binary trees search 35 / 100 / 300 nodes
     // deep (nice 75 / 150 / 258); a chain of 3-byte hashes has to walk further to see the same matches
@@ -937,8 +964,26 @@ __device__ __forceinline__ HcParams nos_params(int level)
     if (level <= 10) { p.max_depth = 250; p.nice_len = 75; }
     else if (level == 11) { p.max_depth = 400; p.nice_len = 150; }
     else { p.max_depth = 600; p.nice_len = 258; }
+#ifdef BDF_NOS_H4
+    // chains of 4-byte hashes behind one 3-byte candidate: the same matches at a fraction of the depth
+    if (level <= 10) p.max_depth = BDF_NOS_H4_D10;
+    else if (level == 11) p.max_depth = BDF_NOS_H4_D11;
+    else p.max_depth = BDF_NOS_H4_D12;
+#endif
+    if (depth_override > 0) p.max_depth = (uint32_t)depth_override;      // experiments (BDF_NOS_DEPTH)
     p.lazy = 0;
     return p;
+}
+
+// 3-byte chains first (only the closest candidate of every position is kept, in global memory), then
+// the 4-byte chains the search walks
+__device__ __forceinline__ void nos_build_chains_h4(HcsSmem &sm, const HcsStream &st, uint16_t *near3)
+{
+    hcs_build_chains<false>(sm, st);
+    for (uint32_t i = threadIdx.x; i < 65536 / 8; i += HCS_THREADS)
+        reinterpret_cast<uint4 *>(near3)[i] = reinterpret_cast<const uint4 *>(sm.link)[i];
+    __syncthreads();
+    hcs_build_chains<true>(sm, st);
 }
 
 __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_nos_kernel(DeflateArgs a)
@@ -947,7 +992,7 @@ __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_nos_kernel(DeflateArgs
     HcsSmem &sm = *reinterpret_cast<HcsSmem *>(smem_raw);
     __shared__ unsigned long long s_idx;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const HcParams prm = nos_params(a.level);
+    const HcParams prm = nos_params(a.level, a.nos_depth);
     uint8_t *slab = static_cast<uint8_t *>(a.scratch) + a.scratch_stride * blockIdx.x;
     uint32_t *recs = reinterpret_cast<uint32_t *>(slab);
     uint32_t *gbest = reinterpret_cast<uint32_t *>(slab + HCS_SCRATCH_PER_CTA);
@@ -971,7 +1016,13 @@ __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_nos_kernel(DeflateArgs
         const uint32_t len = (uint32_t)len64;
         HcsStream st;
         st.set(gin, len);
+        uint16_t *near3 = nullptr;
+#ifdef BDF_NOS_H4
+        near3 = reinterpret_cast<uint16_t *>(lists + (size_t)65536 * HCS_NLIST);
+        nos_build_chains_h4(sm, st, near3);
+#else
         hcs_build_chains(sm, st);
+#endif
         hcs_stage_input(sm, st);
         CtaSink<false> sink;
         if (warp == 0) frame_header(a.format, a.level, out, lane);
@@ -982,7 +1033,7 @@ __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_nos_kernel(DeflateArgs
         // ---- every position: best match and match list
         for (uint32_t pos0 = 0; pos0 < len; pos0 += HCS_SEARCH) {
             const uint32_t ns = len - pos0 < HCS_SEARCH ? len - pos0 : HCS_SEARCH;
-            hcs_search<true>(sm, len, prm, pos0, ns, lists);
+            hcs_search<true>(sm, len, prm, pos0, ns, lists, near3);
             __syncthreads();
             for (uint32_t i = tid; i < ns; i += HCS_THREADS) gbest[pos0 + i] = sm.w.res[i];
             if (tid == 0) sm.c_search_next = 0;

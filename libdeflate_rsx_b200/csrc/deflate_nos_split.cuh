@@ -40,6 +40,7 @@ struct NosWave {
 };
 struct NosSlab {
     uint32_t *recs, *gbest, *choice, *lists;
+    uint16_t *near3;
     NosPlan *plan;
     __device__ __forceinline__ NosSlab(const DeflateArgs &a, uint32_t slot)
     {
@@ -48,6 +49,7 @@ struct NosSlab {
         gbest = reinterpret_cast<uint32_t *>(slab + HCS_SCRATCH_PER_CTA);
         choice = gbest + 65536;
         lists = choice + 65536;
+        near3 = reinterpret_cast<uint16_t *>(lists + (size_t)65536 * HCS_NLIST);
         plan = reinterpret_cast<NosPlan *>(slab + NOS_SCRATCH_PER_CTA);
     }
 };
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_nos_search_kernel(Defl
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HcsSmem &sm = *reinterpret_cast<HcsSmem *>(smem_raw);
     const unsigned tid = threadIdx.x;
-    const HcParams prm = nos_params(a.level);
+    const HcParams prm = nos_params(a.level, a.nos_depth);
     for (uint32_t slot = blockIdx.x; slot < wv.count; slot += gridDim.x) {
         __syncthreads();
         const unsigned long long idx = (unsigned long long)wv.first + slot;
@@ -72,13 +74,19 @@ __global__ void __launch_bounds__(HCS_THREADS, 1) deflate_nos_search_kernel(Defl
         const uint32_t len = (uint32_t)len64;
         HcsStream st;
         st.set(gin, len);
+        const uint16_t *near3 = nullptr;
+#ifdef BDF_NOS_H4
+        nos_build_chains_h4(sm, st, sl.near3);
+        near3 = sl.near3;
+#else
         hcs_build_chains(sm, st);
+#endif
         hcs_stage_input(sm, st);
         if (tid == 0) sm.c_search_next = 0;
         __syncthreads();
         for (uint32_t pos0 = 0; pos0 < len; pos0 += HCS_SEARCH) {
             const uint32_t ns = len - pos0 < HCS_SEARCH ? len - pos0 : HCS_SEARCH;
-            hcs_search<true>(sm, len, prm, pos0, ns, sl.lists);
+            hcs_search<true>(sm, len, prm, pos0, ns, sl.lists, near3);
             __syncthreads();
             for (uint32_t i = tid; i < ns; i += HCS_THREADS) sl.gbest[pos0 + i] = sm.w.res[i];
             if (tid == 0) sm.c_search_next = 0;
