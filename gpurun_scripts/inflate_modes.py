@@ -16,13 +16,17 @@ import libdeflate_rsx_b200 as b
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 want = sys.argv[2:] or ["group", "lane0", "lane1", "auto"]
 ENV = {"group": {"BDF_INFLATE_MODE": "group"}, "lane0": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "0"},
-       "lane1": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "1"}, "lane2": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "2"}, "auto": {"BDF_INFLATE_MODE": "auto"},
+       "lane1": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "1"}, "lane2": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "2"}, "auto": {"BDF_INFLATE_MODE": "auto"}, "auto0": {"BDF_INFLATE_MODE": "auto", "BDF_LANE_CFG": "0"},
        # the same without the first-block header pre-pass (inflate_prehdr.cuh)
        "auto_nopre": {"BDF_INFLATE_MODE": "auto", "BDF_INFLATE_PREHDR": "0"},
        "group_nopre": {"BDF_INFLATE_MODE": "group", "BDF_INFLATE_PREHDR": "0"},
        "serial1": {"BDF_INFLATE_MODE": "auto", "BDF_INFLATE_SERIAL": "1"},
        "serial2": {"BDF_INFLATE_MODE": "auto", "BDF_INFLATE_SERIAL": "2"},
        "concurrent": {"BDF_INFLATE_MODE": "auto", "BDF_INFLATE_SERIAL": "0"},
+       "lane3": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "3"}, "lane4": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "4"},
+       "lane5": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "5"}, "auto5": {"BDF_INFLATE_MODE": "auto", "BDF_LANE_CFG": "5"},
+       "lane3w12": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "3", "BDF_LANE_WARPS": "12"},
+       "lane3w10": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "3", "BDF_LANE_WARPS": "10"},
        "lane0_nopre": {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "0", "BDF_INFLATE_PREHDR": "0"}}
 dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(dev)
@@ -34,7 +38,7 @@ KINDS = {
 }
 ctxs = {}
 for m in want:
-    for k in ("BDF_INFLATE_MODE", "BDF_LANE_CFG", "BDF_INFLATE_PREHDR", "BDF_INFLATE_SERIAL"):
+    for k in ("BDF_INFLATE_MODE", "BDF_LANE_CFG", "BDF_INFLATE_PREHDR", "BDF_INFLATE_SERIAL", "BDF_LANE_WARPS"):
         os.environ.pop(k, None)
     os.environ.update(ENV[m])
     ctxs[m] = b.Context(0)

@@ -63,7 +63,7 @@ struct bdf_ctx {
     int inflate_group = 16;                     // lanes per stream in inflate_kernel (BDF_INFLATE_GROUP)
     int inflate_mode = 0;                       // 0 = both engines, split by expansion ratio; 1 = lane groups only; 2 = lane per stream only (BDF_INFLATE_MODE)
     int inflate_split = 16;                     // expansion ratio from which a stream goes to the lane-group kernel (BDF_INFLATE_SPLIT)
-    int lane_cfg = 0;                           // direct-table bits of inflate_lane_kernel: 0 = (8, 7), 7 warps / SM; 1 = (9, 6), 5 warps / SM; 2 = (8, 6), 8 warps / SM (BDF_LANE_CFG)
+    int lane_cfg = 5;                           // inflate_lane_kernel tables: 0 = (8, 7) bits in shared memory, 7 warps / SM; 1 = (9, 6), 5 warps; 2 = (8, 6), 8 warps; 3 / 4 = (8, 7) / (9, 7) in global memory behind L1, 16 warps; 5 = 4 with the litlen width chosen per block, 8 or 9 bits (BDF_LANE_CFG)
     int inflate_serial = 1;                     // the two engines of a call: 1 = lane groups, then lanes, on the caller's stream; 2 = the other order; 0 = side by side on two streams (BDF_INFLATE_SERIAL)
     int inflate_prehdr = 1;                     // first-block headers decoded by inflate_prehdr_kernel ahead of the engines (BDF_INFLATE_PREHDR=0: off)
     int lane_warps_per_sm = 0;                  // cap on resident warps of inflate_lane_kernel, 0 = what fits (BDF_LANE_WARPS)
@@ -160,25 +160,27 @@ int launch_inflate_g(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
     return 0;
 }
 
-template <int FORMAT, int LTB, int OTB>
+template <int FORMAT, int LTB, int OTB, bool GT = false, bool ADAPT = false>
 int launch_inflate_lane_c(bdf_ctx *ctx, bdf::InflateArgs a, cudaStream_t s)
 {
-    const size_t smem = sizeof(bdf::LaneSmem<LTB, OTB>);
+    const size_t smem = sizeof(bdf::LaneSmem<LTB, OTB, GT>);
     int &bps = ctx->lane_blocks_per_sm[FORMAT];
     if (bps == 0) {
-        CK(cudaFuncSetAttribute(bdf::inflate_lane_kernel<FORMAT, LTB, OTB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(bdf::inflate_lane_kernel<FORMAT, LTB, OTB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, bdf::inflate_lane_kernel<FORMAT, LTB, OTB>, 32, smem));
+        CK(cudaFuncSetAttribute(bdf::inflate_lane_kernel<FORMAT, LTB, OTB, GT, ADAPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // tables in global memory: leave the L1 as large as the shared memory in use allows
+        if (!GT) CK(cudaFuncSetAttribute(bdf::inflate_lane_kernel<FORMAT, LTB, OTB, GT, ADAPT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, bdf::inflate_lane_kernel<FORMAT, LTB, OTB, GT, ADAPT>, 32, smem));
         if (bps < 1) bps = 1;
         if (ctx->lane_warps_per_sm > 0 && ctx->lane_warps_per_sm < bps) bps = ctx->lane_warps_per_sm;
     }
     unsigned long long want = ((unsigned long long)a.n + 31) / 32;
     unsigned long long full = (unsigned long long)ctx->sm_count * bps;
     unsigned grid = (unsigned)(want < full ? want : full);
-    int rc = ensure(ctx, ctx->lane_scratch, (size_t)full * 32 * bdf::LANE_SORTED_BYTES);
+    // the tables (GT) sit behind the symbol lists of the LAUNCHED grid: the kernel finds them from gridDim
+    int rc = ensure(ctx, ctx->lane_scratch, (size_t)full * 32 * (bdf::LANE_SORTED_BYTES + (GT ? sizeof(bdf::LaneTab<LTB, OTB>) : 0)));
     if (rc) return rc;
     a.lane_scratch = (uint8_t *)ctx->lane_scratch.p;
-    bdf::inflate_lane_kernel<FORMAT, LTB, OTB><<<grid, 32, smem, s>>>(a);
+    bdf::inflate_lane_kernel<FORMAT, LTB, OTB, GT, ADAPT><<<grid, 32, smem, s>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -187,9 +189,12 @@ int launch_inflate_lane_c(bdf_ctx *ctx, bdf::InflateArgs a, cudaStream_t s)
 template <int FORMAT>
 int launch_inflate_lane(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
 {
+    if (ctx->lane_cfg == 0) return launch_inflate_lane_c<FORMAT, 8, 7>(ctx, a, s);
     if (ctx->lane_cfg == 1) return launch_inflate_lane_c<FORMAT, 9, 6>(ctx, a, s);
     if (ctx->lane_cfg == 2) return launch_inflate_lane_c<FORMAT, 8, 6>(ctx, a, s);
-    return launch_inflate_lane_c<FORMAT, 8, 7>(ctx, a, s);
+    if (ctx->lane_cfg == 3) return launch_inflate_lane_c<FORMAT, 8, 7, true>(ctx, a, s);
+    if (ctx->lane_cfg == 4) return launch_inflate_lane_c<FORMAT, 9, 7, true>(ctx, a, s);
+    return launch_inflate_lane_c<FORMAT, 9, 7, true, true>(ctx, a, s);
 }
 
 template <int FORMAT>
@@ -279,7 +284,7 @@ int bdf_ctx_create(int device, bdf_ctx **out)
         int v = atoi(e);
         if (v >= 1 && v <= 1032) ctx->inflate_split = v;
     }
-    if (const char *e = getenv("BDF_LANE_CFG")) ctx->lane_cfg = atoi(e) >= 0 && atoi(e) <= 2 ? atoi(e) : 0;
+    if (const char *e = getenv("BDF_LANE_CFG")) ctx->lane_cfg = atoi(e) >= 0 && atoi(e) <= 5 ? atoi(e) : 5;
     if (const char *e = getenv("BDF_INFLATE_PREHDR")) ctx->inflate_prehdr = atoi(e) != 0;
     if (const char *e = getenv("BDF_INFLATE_SERIAL")) ctx->inflate_serial = atoi(e);
     if (const char *e = getenv("BDF_LANE_WARPS")) ctx->lane_warps_per_sm = atoi(e) > 0 ? atoi(e) : 0;

@@ -46,9 +46,12 @@ struct LaneTab {                    // one per lane (stream slot)
     uint16_t off_tab[1 << OTB];
     uint32_t pad;                   // odd stride in words: equal indices of different lanes fall into different banks
 };
-template <int LTB, int OTB>
+// GT: the per-lane tables live in GLOBAL memory (lane_scratch, read through L1) instead of shared
+// memory: what is left in shared memory is 6.4 KB per warp, so registers (16 warps per SM) and not
+// shared memory (7) decide how many streams an SM holds.
+template <int LTB, int OTB, bool GT = false>
 struct LaneSmem {                   // one per warp
-    LaneTab<LTB, OTB> tab[32];
+    LaneTab<LTB, OTB> tab[GT ? 1 : 32];
     uint4 ring[32][(LANE_RING + 16) / 16];  // + 16: a copy step may spill up to 16 bytes past the end
     HuffCode lit_code, off_code;    // of the block whose header was read last
     BuildScratch<32> bs;
@@ -138,9 +141,14 @@ struct LongCodes {
     }
 };
 
-template <int FORMAT, int LTB, int OTB>
-__global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
+// ADAPT (with GT): the litlen table of a block is 8 or 9 bits wide — LTB is the room a lane has, the
+// width is chosen per block from the weight of the codewords an 8-bit table would miss (Kraft mass of
+// the lengths above 8): binary records put ~40 % of their symbols there, text a few percent, and a
+// 9-bit table that is not needed doubles what a lane keeps in L1.
+template <int FORMAT, int LTB, int OTB, bool GT = false, bool ADAPT = false>
+__global__ void __launch_bounds__(32, GT ? 16 : 1) inflate_lane_kernel(InflateArgs a)
 {
+    static_assert(!ADAPT || (GT && LTB == 9), "adaptive width: 8 or 9 bits in a 9-bit table in global memory");
     constexpr int RING = LANE_RING;
     constexpr uint32_t MASK = RING - 1, WMASK = RING / 4 - 1;
     // A copy step rewrites up to 20 bytes from the word pos lies in, i.e. it may clobber ring
@@ -153,12 +161,16 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
     constexpr uint32_t FLUSH_AT = 56;             // < COPY_MAX - 16: a lane that reaches it still has a round of room
     constexpr bool ADLER = FORMAT == BDF_ZLIB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    LaneSmem<LTB, OTB> &sm = *reinterpret_cast<LaneSmem<LTB, OTB> *>(smem_raw);
-    using LaneSmemT = LaneSmem<LTB, OTB>;
+    LaneSmem<LTB, OTB, GT> &sm = *reinterpret_cast<LaneSmem<LTB, OTB, GT> *>(smem_raw);
+    using LaneSmemT = LaneSmem<LTB, OTB, GT>;
     static_assert(offsetof(LaneSmemT, lens) % 4 == 0, "load_code_lengths stores words");
     const unsigned lane = threadIdx.x;
     const Grp<32> g;
-    LaneTab<LTB, OTB> &T = sm.tab[lane];
+    // GT: the tables of the warp's 32 slots sit behind the symbol lists of the warp's scratch
+    LaneTab<LTB, OTB> *const tabs = GT ? reinterpret_cast<LaneTab<LTB, OTB> *>(
+                                             a.lane_scratch + (size_t)gridDim.x * 32 * LANE_SORTED_BYTES) + (size_t)blockIdx.x * 32
+                                       : sm.tab;
+    LaneTab<LTB, OTB> &T = tabs[lane];
     uint8_t *const ring = reinterpret_cast<uint8_t *>(sm.ring[lane]);
     uint32_t *const ringw = reinterpret_cast<uint32_t *>(ring);
     uint16_t *const my_sorted = reinterpret_cast<uint16_t *>(
@@ -167,7 +179,8 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
     // ---- per-lane stream state
     BitReader br;
     br.p = a.in; br.len = 0; br.mis = 0; br.nwords = 0; br.widx = 0; br.ahead = 0; br.buf = 0; br.left = 0;
-    LongCodes<LTB + 1> lcode;
+    LongCodes<ADAPT ? 9 : LTB + 1> lcode;
+    uint32_t lmask = (1u << LTB) - 1u;       // ADAPT: mask of the width the current block's table was built with
     LongCodes<OTB + 1> ocode;
     lcode.load(sm.lit_code); ocode.load(sm.off_code);      // (values are replaced before they are used)
     const uint8_t *sp = a.in;        // stream start (framing included)
@@ -305,8 +318,8 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                 uint32_t pm = __shfl_sync(BDF_FULL_MASK, pre_meta, s);
                 const uint32_t *prow = a.hdr_rows + (size_t)__shfl_sync(BDF_FULL_MASK, idx, s) * PREHDR_ROW_WORDS;
                 int hst = BDF_OK;           // status that ends the stream (uniform)
-                bool ended = false, fin = false;
-                LaneTab<LTB, OTB> &Ts = sm.tab[s];
+                bool ended = false, fin = false, narrow = false;
+                LaneTab<LTB, OTB> &Ts = tabs[s];
                 uint16_t *sorted_s = reinterpret_cast<uint16_t *>(
                     a.lane_scratch + ((size_t)blockIdx.x * 32 + s) * LANE_SORTED_BYTES);
                 LaneView v{Ts.lit_tab, Ts.off_tab, sorted_s, sorted_s + 288, sm.lit_code, sm.off_code, sm.bs, sm.lens};
@@ -320,7 +333,7 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                         type = b.take(2);
                     }
                     if (type == 1) {
-                        load_static_codes<32, LaneView, LTB, OTB>(g, v);
+                        load_static_codes<32, LaneView, LTB, OTB>(g, v);       // 112 of its literals have 9-bit codes
                         break;
                     }
                     if (type == 2) {
@@ -328,7 +341,20 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                         unsigned nlit = 0, noff = 0;
                         if (pm & PREHDR_VALID) load_code_lengths<32, LaneView>(g, b, v, pm, prow, nlit, noff);
                         else hst = read_code_lengths<32, LaneView, LTB, OTB>(g, b, v, nlit, noff);
-                        if (hst == BDF_OK) hst = build_dynamic_codes<32, LaneView, LTB, OTB>(g, v, nlit, noff, nlong);
+                        if (ADAPT && hst == BDF_OK) {
+                            // Kraft mass (units of 2^-15) of the litlen codewords longer than 8 bits
+                            uint32_t mass = 0;
+                            for (unsigned q = lane; q < nlit; q += 32) {
+                                const unsigned l = sm.lens[q];
+                                if (l > 8) mass += 1u << (15 - l);
+                            }
+#pragma unroll
+                            for (int d = 16; d > 0; d >>= 1) mass += __shfl_xor_sync(BDF_FULL_MASK, mass, d);
+                            narrow = mass < (1u << 15) / 8;              // < 12.5 % of the symbols: 8 bits
+                        }
+                        if (hst == BDF_OK)
+                            hst = (ADAPT && narrow) ? build_dynamic_codes<32, LaneView, 8, OTB>(g, v, nlit, noff, nlong)
+                                                    : build_dynamic_codes<32, LaneView, LTB, OTB>(g, v, nlit, noff, nlong);
                         if (hst != BDF_OK) ended = true;
                         break;
                     }
@@ -385,6 +411,7 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                         st = LS_RUN;
                         lcode.load(sm.lit_code);
                         ocode.load(sm.off_code);
+                        if (ADAPT) lmask = narrow ? 255u : 511u;
                     }
                 }
                 __syncwarp();               // before the next header overwrites the code descriptions
@@ -449,7 +476,7 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                 if (br.left <= 32 && br.widx > br.nwords + 2) { status = BDF_SHORT_INPUT; st = LS_END; }
                 else {
                     lane_refill(br);
-                    uint32_t e = T.lit_tab[br.peek(LTB)];
+                    uint32_t e = T.lit_tab[ADAPT ? ((uint32_t)br.buf & lmask) : br.peek(LTB)];
                     if (e & LITFLAG) {
                         if (pos >= cap) { status = BDF_INSUFFICIENT_SPACE; st = LS_END; }
                         else {
@@ -457,7 +484,7 @@ __global__ void __launch_bounds__(32) inflate_lane_kernel(InflateArgs a)
                             pos++;
                             br.drop(e & E_LEN);
                             // literals come in runs: the second look-up needs no refill (>= 25 valid bits)
-                            e = T.lit_tab[br.peek(LTB)];
+                            e = T.lit_tab[ADAPT ? ((uint32_t)br.buf & lmask) : br.peek(LTB)];
                             if ((e & LITFLAG) && pos < cap) {
                                 ring[(pos + rbias) & MASK] = (uint8_t)(e >> E_VAL);
                                 pos++;
