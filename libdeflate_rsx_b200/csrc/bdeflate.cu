@@ -59,13 +59,14 @@ struct bdf_ctx {
     unsigned long long *d_counters = nullptr;   // work-queue heads, one slot per launch in flight
     unsigned counter_slot = 0;
     int inflate_blocks_per_sm[3] = {0, 0, 0};
-    int lane_blocks_per_sm[3] = {0, 0, 0};
+    int lane_blocks_per_sm[3][2] = {};          // [format][tables in global memory]
     int inflate_group = 16;                     // lanes per stream in inflate_kernel (BDF_INFLATE_GROUP)
     int inflate_mode = 0;                       // 0 = both engines, split by expansion ratio; 1 = lane groups only; 2 = lane per stream only (BDF_INFLATE_MODE)
     int inflate_split = 16;                     // expansion ratio from which a stream goes to the lane-group kernel (BDF_INFLATE_SPLIT)
     int lane_cfg = 5;                           // inflate_lane_kernel tables: 0 = (8, 7) bits in shared memory, 7 warps / SM; 1 = (9, 6), 5 warps; 2 = (8, 6), 8 warps; 3 / 4 = (8, 7) / (9, 7) in global memory behind L1, 16 warps; 5 = 4 with the litlen width chosen per block, 8 or 9 bits (BDF_LANE_CFG)
     int inflate_serial = 1;                     // the two engines of a call: 1 = lane groups, then lanes, on the caller's stream; 2 = the other order; 0 = side by side on two streams (BDF_INFLATE_SERIAL)
     int inflate_prehdr = 1;                     // first-block headers decoded by inflate_prehdr_kernel ahead of the engines (BDF_INFLATE_PREHDR=0: off)
+    bool lane_cfg_auto = true;                  // BDF_LANE_CFG not set: small batches take the shared-memory tables (see launch_inflate_lane)
     int lane_warps_per_sm = 0;                  // cap on resident warps of inflate_lane_kernel, 0 = what fits (BDF_LANE_WARPS)
     bdf::DeflateScratch deflate_scratch;
     DevBuf in, out, in_off, out_off, max_out, out_size, status, checksum, lane_scratch, dense, dense_off, hdr_rows, hdr_meta;
@@ -164,7 +165,7 @@ template <int FORMAT, int LTB, int OTB, bool GT = false, bool ADAPT = false>
 int launch_inflate_lane_c(bdf_ctx *ctx, bdf::InflateArgs a, cudaStream_t s)
 {
     const size_t smem = sizeof(bdf::LaneSmem<LTB, OTB, GT>);
-    int &bps = ctx->lane_blocks_per_sm[FORMAT];
+    int &bps = ctx->lane_blocks_per_sm[FORMAT][GT ? 1 : 0];
     if (bps == 0) {
         CK(cudaFuncSetAttribute(bdf::inflate_lane_kernel<FORMAT, LTB, OTB, GT, ADAPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // tables in global memory: leave the L1 as large as the shared memory in use allows
@@ -189,7 +190,11 @@ int launch_inflate_lane_c(bdf_ctx *ctx, bdf::InflateArgs a, cudaStream_t s)
 template <int FORMAT>
 int launch_inflate_lane(bdf_ctx *ctx, const bdf::InflateArgs &a, cudaStream_t s)
 {
-    if (ctx->lane_cfg == 0) return launch_inflate_lane_c<FORMAT, 8, 7>(ctx, a, s);
+    // Tables in global memory pay off through the streams they let an SM hold (16 warps instead of 7); a
+    // batch that fits the shared-memory variant in one go is faster there (mixed pipeline of bench.py,
+    // 24576 light streams = 768 warps: 66 GB/s against 60).
+    if (ctx->lane_cfg == 0 || (ctx->lane_cfg_auto && ((unsigned long long)a.n + 31) / 32 <= 7ull * (unsigned long long)ctx->sm_count))
+        return launch_inflate_lane_c<FORMAT, 8, 7>(ctx, a, s);
     if (ctx->lane_cfg == 1) return launch_inflate_lane_c<FORMAT, 9, 6>(ctx, a, s);
     if (ctx->lane_cfg == 2) return launch_inflate_lane_c<FORMAT, 8, 6>(ctx, a, s);
     if (ctx->lane_cfg == 3) return launch_inflate_lane_c<FORMAT, 8, 7, true>(ctx, a, s);
@@ -284,7 +289,7 @@ int bdf_ctx_create(int device, bdf_ctx **out)
         int v = atoi(e);
         if (v >= 1 && v <= 1032) ctx->inflate_split = v;
     }
-    if (const char *e = getenv("BDF_LANE_CFG")) ctx->lane_cfg = atoi(e) >= 0 && atoi(e) <= 5 ? atoi(e) : 5;
+    if (const char *e = getenv("BDF_LANE_CFG")) { ctx->lane_cfg = atoi(e) >= 0 && atoi(e) <= 5 ? atoi(e) : 5; ctx->lane_cfg_auto = false; }
     if (const char *e = getenv("BDF_INFLATE_PREHDR")) ctx->inflate_prehdr = atoi(e) != 0;
     if (const char *e = getenv("BDF_INFLATE_SERIAL")) ctx->inflate_serial = atoi(e);
     if (const char *e = getenv("BDF_LANE_WARPS")) ctx->lane_warps_per_sm = atoi(e) > 0 ? atoi(e) : 0;

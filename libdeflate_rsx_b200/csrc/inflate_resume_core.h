@@ -287,7 +287,10 @@ BDF_HD int resume_step(bdf_inflate_state &S, const uint8_t *in, uint64_t in_len,
         }
         // ---- PH_HUFF
         if (!tables_ready) {
-            if (S.nlit > 288 || S.noff > 32 || !build_block_tables(S, T)) { S.phase = PH_FAILED; RS_RETURN(BDF_BAD_DATA); }
+            // the state is the caller's memory: nothing in it is trusted
+            bool sane = S.nlit >= 257 && S.nlit <= 288 && S.noff >= 1 && S.noff <= 32;
+            for (uint32_t s = 0; sane && s < S.nlit + S.noff; s++) sane = S.lens[s] <= 15;
+            if (!sane || !build_block_tables(S, T)) { S.phase = PH_FAILED; RS_RETURN(BDF_BAD_DATA); }
             tables_ready = true;
         }
         for (;;) {

@@ -16,6 +16,7 @@ VARIANTS = [
     {"BDF_HC_KERNEL": "old", "BDF_INFLATE_MODE": "group"},
     {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "0"},          # tables in shared memory (the default keeps them in global memory)
     {"BDF_LANE_CFG": "3"},
+    {"BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "5"},          # global tables, width per block (the default only for large batches)
     {"BDF_HC_KERNEL": "new", "BDF_INFLATE_MODE": "lane", "BDF_LANE_CFG": "1"},
     {"BDF_HC_KERNEL": "old", "BDF_HC_CTAS_PER_SM": "3", "BDF_INFLATE_MODE": "group", "BDF_INFLATE_GROUP": "32"},
     {"BDF_INFLATE_MODE": "auto", "BDF_INFLATE_SPLIT": "4", "BDF_LANE_WARPS": "3"},

@@ -203,3 +203,19 @@ def test_step_contract_directly():
     assert bytes(out) == p
     assert int.from_bytes(st[40:48], "little") == len(p)             # total_out
     assert int.from_bytes(st[32:40], "little") + len(pending) == len(comp)      # total_in
+
+
+def test_tampered_state_is_rejected():
+    """the state is plain caller-owned memory: a resumed state with impossible fields fails cleanly"""
+    comp = raw(corpus.text_stream(2, 60000))
+    for field, value in (("lens", 200), ("nlit", 400), ("noff", 0), ("bit_off", 9), ("phase", 7)):
+        st = bytearray(stream.STATE_BYTES)
+        win = np.zeros(70000, dtype=np.uint8)
+        status, used, pos = resume_host.step(st, comp[:3000], False, win, 0)
+        assert status == SHORT_INPUT and int.from_bytes(st[0:4], "little") == 2        # inside a Huffman block
+        if field == "lens":
+            st[48 + 5] = value
+        else:
+            off = {"phase": 0, "bit_off": 8, "nlit": 16, "noff": 20}[field]
+            st[off:off + 4] = value.to_bytes(4, "little")
+        assert resume_host.step(st, comp[used:], True, win, pos)[0] == BAD_DATA
