@@ -205,6 +205,26 @@ __global__ void __launch_bounds__(NOS_COST_WARPS * 32) deflate_nos_cost_kernel(D
             const uint32_t e = mine ? cur : 0u;
             uint32_t litc = 0;
             if (g == 3 && k < 3 && hi >= block_start + 1 + k) litc = S.lit_cost[cur & 0xFFu];
+            if (!__any_sync(BDF_FULL_MASK, e != 0)) {
+                // no match starts at any of the three positions: literals only
+                const uint32_t l0 = __shfl_sync(BDF_FULL_MASK, litc, 24), l1 = __shfl_sync(BDF_FULL_MASK, litc, 25),
+                               l2 = __shfl_sync(BDF_FULL_MASK, litc, 26);
+                if (lane == 0) {
+                    uint32_t c = S.ring[hi & 511u];
+                    const uint32_t ll[3] = {l0, l1, l2};
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        if (hi >= block_start + 1u + j) {
+                            const uint32_t qq = hi - 1 - j;
+                            c += ll[j];
+                            S.ring[qq & 511u] = c;
+                            sl.choice[qq] = 1u;
+                        }
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
             const uint32_t e_prev = __shfl_up_sync(BDF_FULL_MASK, e, 1);
             uint32_t v = NOS_INF << 4, vlen = 0;
             if (e) {
