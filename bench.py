@@ -295,7 +295,9 @@ def compress_section(env, level, n, steps, e2e_steps, cpu_sample, cpu_seconds, w
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     kname = ("bdf::deflate_l1_kernel" if level == 1 else "bdf::deflate_hc_kernel (corpus A is periodic: the classifier "
-             "sends it there)" if level <= 9 else "bdf::deflate_nos_kernel")
+             "sends it there)" if level <= 9 else
+             "bdf::deflate_nos_cost_kernel (dominant: 18.5 of the 35 ms) + deflate_nos_search_kernel + deflate_nos_emit_kernel; "
+             "traffic is the cost kernel's")
     sec = {
         "workload": f"compress {n} x 64 KiB of corpus A (gen_bench) per GPU at level {level}, raw DEFLATE; "
                     + ("byte-identical to the oracle" if level <= 9 else "total size <= 1.005 x the oracle's, zlib round trip"),
