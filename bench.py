@@ -208,6 +208,51 @@ def cpu_compress(o, flat, in_off, n, level, fmt, min_seconds):
     return int(sub_off[-1]) / best / 1e9, cores, reps, (out, out_off, out_size)
 
 
+def l1_text_probe(env, d_slab, d_slab_off, d_size, d_stat, bound, steps, n_max):
+    """Level 1 on NON-periodic data (corpus A is a run of 258-byte matches, the easy case of this parse):
+    8192 x 64 KiB of the text kind of corpus B per GPU, 64 distinct streams, byte-identical to the
+    oracle, device-resident (CUDA events)."""
+    import torch
+    import corpus
+    import oracle_lib as o
+    ctx, lib, bdf, dev, stream, world = env["ctx"], env["lib"], env["bdf"], env["dev"], env["stream"], env["world"]
+    n = min(n_max, 8192) // 64 * 64
+    plain = [corpus.text_stream(k) for k in range(64)]
+    tile = torch.from_numpy(np.frombuffer(b"".join(plain), dtype=np.uint8).copy()).to(dev)
+    d_plain = tile.repeat(n // 64)
+    d_in_off = torch.arange(n + 1, dtype=torch.int64, device=dev) * STREAM
+    sp = C.c_void_p(stream.cuda_stream)
+
+    def step():
+        ctx.check(lib.bdf_compress_batch_device(ctx.handle, 1, bdf.RAW, d_plain.data_ptr(), d_in_off.data_ptr(), n,
+                                                d_slab.data_ptr(), d_slab_off.data_ptr(), d_size.data_ptr(),
+                                                d_stat.data_ptr(), sp))
+    d_stat[:n].fill_(-1)
+    step()
+    torch.cuda.synchronize(dev)
+    assert int((d_stat[:n] != 0).sum()) == 0
+    sizes = d_size[:n].cpu().numpy()
+    got = [d_slab[k * bound:k * bound + int(sizes[k])].cpu().numpy().tobytes() for k in range(64)]
+    assert got == [o.compress(p, 1) for p in plain], "level 1 on text: output differs from the oracle"
+    assert (sizes.reshape(-1, 64) == sizes[:64]).all()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    env["barrier"]()
+    ev[0].record(stream)
+    for _ in range(steps):
+        step()
+    ev[1].record(stream)
+    env["barrier"]()
+    t = torch.tensor([ev[0].elapsed_time(ev[1]) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        env["dist"].all_reduce(t, op=env["dist"].ReduceOp.MAX)
+    ms = float(t.item())
+    comp = int(sizes.sum())
+    return {"workload": f"compress {n} x 64 KiB of text (corpus B's text kind) per GPU at level 1, raw DEFLATE; byte-identical to the oracle",
+            "unit": "GB/s (uncompressed)", "value": world * n * STREAM / (ms * 1e-3) / 1e9, "kernel_ms": ms, "steps": steps,
+            "ratio": n * STREAM / comp,
+            "roofline": roofline("bdf::deflate_l1_kernel (whole-window rounds)", n * STREAM + comp, ms, n, "deflate_l1_text_window")}
+
+
 def compress_section(env, level, n, steps, e2e_steps, cpu_sample, cpu_seconds, with_cpu):
     """BASELINE configs[2] / [3]: n x 64 KiB of corpus A at `level`, raw DEFLATE, device-resident
     (CUDA events) and through the host call; checked against the oracle inside the bench."""
@@ -262,6 +307,7 @@ def compress_section(env, level, n, steps, e2e_steps, cpu_sample, cpu_seconds, w
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     ubytes = n * STREAM
+    text = l1_text_probe(env, d_slab, d_slab_off, d_size, d_stat, bound, steps, n) if level == 1 and n >= 64 else None
     del d_slab
     torch.cuda.empty_cache()
 
@@ -308,6 +354,8 @@ def compress_section(env, level, n, steps, e2e_steps, cpu_sample, cpu_seconds, w
                 "h2d_bytes_per_step": ubytes + (n + 1) * 8, "d2h_bytes_per_step": comp_bytes + (n + 1) * 8 + n * 4,
                 "api": "bdf_compress_batch_host_dense (pinned host buffers)"},
     }
+    if text:
+        sec["text"] = text
     if with_cpu:
         ns = min(n, cpu_sample)
         v, cores, reps, (oo, ooff, osz) = cpu_compress(o, h_in, h_in_off, ns, level, o.RAW, cpu_seconds)

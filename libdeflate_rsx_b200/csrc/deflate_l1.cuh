@@ -21,6 +21,7 @@ namespace bdf {
 
 constexpr int L1_WARPS = 4;                      // streams per CTA
 constexpr int L1_RUN_BATCH = 8;                  // matches of a speculated run verified per memory round trip
+constexpr uint32_t L1_SPEC_CAP = 16;             // bytes of a match every lane measures ahead of the window walk
 
 // The hash table of each stream (last position per bucket, all-ones = empty; 16-bit positions
 // for the 64 KiB instance, 32-bit for the 256 KiB one) lives in a per-warp global slab that
@@ -70,8 +71,11 @@ __device__ __forceinline__ void static_off_code(unsigned off, uint32_t &bits, ui
     n = 5 + extra;
 }
 
+#ifndef BDF_L1_MIN_CTAS
+#define BDF_L1_MIN_CTAS 8                        // resident CTAs per SM the register allocation aims at (64 registers)
+#endif
 template <bool BIG, bool SIZE = false>
-__global__ void __launch_bounds__(L1_WARPS * 32) deflate_l1_kernel(DeflateArgs a)
+__global__ void __launch_bounds__(L1_WARPS * 32, BDF_L1_MIN_CTAS) deflate_l1_kernel(DeflateArgs a)
 {
     using CFG = L1Cfg<BIG>;
     using pos_t = typename CFG::pos_t;
@@ -192,6 +196,123 @@ __global__ void __launch_bounds__(L1_WARPS * 32) deflate_l1_kernel(DeflateArgs a
                 }
                 __syncwarp();
                 // the position is not a match at all: the literal speculation takes it from here
+            }
+            if (!split && a.l1_window) {
+                // WHOLE-WINDOW ROUND (tools/l1_window_sim.py states it with plain lists and checks it
+                // against the serial parse).  The 32 lanes read their buckets once, as they were
+                // before the round; bucket writes of the round are stood in for by same-hash lower
+                // lanes (match.any).  The warp then walks the window from match to match without
+                // going back to memory: `inserted` collects the lanes that were really probed
+                // (literals and match starts), lanes from `cur` on count as probed for the lanes
+                // above them, lanes inside a match never enter the table (skip_positions is a
+                // no-op, :1231).  Every lane has measured the match it would have if all lower lanes
+                // were probed (the usual case) up to L1_SPEC_CAP bytes beforehand, so a step of the
+                // walk touches memory only for long matches or for a candidate the speculation
+                // did not foresee.  Up to 32 + 257 bytes per round instead of one match.
+                const uint32_t p = pos + lane;
+                const bool hashable = p + 3 <= len;
+                uint32_t v = 0, h = 0x10000u + lane;
+                if (hashable) { v = ld24(in + p); h = hash3(v); }
+                const unsigned peers = __match_any_sync(BDF_FULL_MASK, h);
+                const unsigned lower = peers & lanemask_lt();
+                const unsigned hmask = __ballot_sync(BDF_FULL_MASK, hashable);
+                uint32_t tc = CFG::EMPTY;
+                if (hashable) tc = table[h];
+                // (experiment, bits 1 / 2 of BDF_L1_WINDOW) the buckets of the NEXT window are prefetched while this
+                // one is worked on: its bytes are requested here and have arrived once the bucket above has
+                uint32_t vn = 0;
+                const bool pn = (a.l1_window & 6) && p + 35 <= len;
+                if (pn) vn = ld24(in + p + 32);
+                const bool tfound = hashable && tc != CFG::EMPTY && p - tc <= 32768u && ld24(in + tc) == v;
+                if (pn) {
+                    const pos_t *nb = table + hash3(vn);
+                    if (a.l1_window & 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(nb));
+                    else asm volatile("prefetch.global.L2 [%0];" ::"l"(nb));
+                }
+                const unsigned jl = lower ? 31 - __clz(lower) : lane;
+                const uint32_t vjl = __shfl_sync(BDF_FULL_MASK, v, jl);
+                uint32_t scand = 0xFFFFFFFFu, slen = 0;
+                if (lower) { if (vjl == v) scand = pos + jl; }
+                else if (tfound) scand = tc;
+                if (scand != 0xFFFFFFFFu) {
+                    const uint32_t room = len - p < 258u ? len - p : 258u;
+                    slen = prefix_len_bytes(in + scand, in + p, room < L1_SPEC_CAP ? room : L1_SPEC_CAP);
+                }
+                unsigned inserted = 0, lit = 0, mm = 0, cur = 0;
+                uint32_t mylen = slen, mycand = scand, nxt = 0, lastlen = 0;
+                // lanes whose candidate depends on what the round itself inserts, and the hits that do not
+                const unsigned depmask = __ballot_sync(BDF_FULL_MASK, lower != 0);
+                const unsigned smask = __ballot_sync(BDF_FULL_MASK, tfound && lower == 0);
+                for (;;) {
+                    const unsigned from_cur = 0xFFFFFFFFu << cur;             // cur < 32 here
+                    const unsigned sh = smask & from_cur;
+                    const unsigned ks = sh ? __ffs(sh) - 1 : 32u;
+                    const unsigned below_ks = sh ? (sh & (0u - sh)) - 1u : 0xFFFFFFFFu;
+                    unsigned k;
+                    uint32_t ck = 0;
+                    bool spec = true;                                         // the match is the one its lane measured
+                    if ((depmask & from_cur & below_ks) == 0) {
+                        // STATIC step: no lane between cur and the first plain hit looks at the round's own
+                        // insertions, so that hit is the next match, with its bucket candidate: bit operations only
+                        if (ks == 32) { lit |= from_cur; inserted |= from_cur; nxt = pos + 32; lastlen = 0; break; }
+                        k = ks;
+                    } else {
+                        const unsigned eff = lower & (inserted | from_cur);
+                        const unsigned j = eff ? 31 - __clz(eff) : lane;
+                        const uint32_t vj = __shfl_sync(BDF_FULL_MASK, v, j);
+                        const bool ok = eff ? vj == v : tfound;
+                        const uint32_t c = eff ? pos + j : tc;
+                        const unsigned fb = __ballot_sync(BDF_FULL_MASK, ok && hashable && lane >= cur);
+                        if (!fb) { lit |= from_cur; inserted |= from_cur; nxt = pos + 32; lastlen = 0; break; }
+                        k = __ffs(fb) - 1;
+                        ck = __shfl_sync(BDF_FULL_MASK, c, k);
+                        spec = ck == __shfl_sync(BDF_FULL_MASK, scand, k);
+                        if (lane == k) mycand = ck;
+                    }
+                    const unsigned seg = from_cur & ((2u << k) - 1u);         // lanes cur..k are probed
+                    lit |= seg & ~(1u << k);
+                    inserted |= seg;
+                    mm |= 1u << k;
+                    const uint32_t slk = __shfl_sync(BDF_FULL_MASK, slen, k);
+                    const uint32_t mp = pos + k;
+                    const uint32_t rk = len - mp < 258u ? len - mp : 258u;
+                    uint32_t mlen = slk;
+                    if (!spec || (slk >= L1_SPEC_CAP && slk < rk)) {
+                        if (spec) {
+                            ck = __shfl_sync(BDF_FULL_MASK, scand, k);
+                            mlen = L1_SPEC_CAP + warp_match_len(in + ck + L1_SPEC_CAP, in + mp + L1_SPEC_CAP, rk - L1_SPEC_CAP, lane);
+                        } else {
+                            mlen = warp_match_len(in + ck, in + mp, rk, lane);
+                        }
+                        if (lane == k) mylen = mlen;
+                    }
+                    BDF_ASSERT(mlen >= 3 && mlen <= rk && mp + mlen <= len);
+                    BDF_ASSERT(lane != k || (mycand < mp && mp - mycand <= 32768u && mylen == mlen));
+                    cur = k + (mlen ? mlen : 1u);                            // mlen >= 3 (the 3 hashed bytes are equal); never stall
+                    lastlen = mlen;
+                    if (cur >= 32) { nxt = pos + cur; break; }
+                }
+                // bucket writes of the probed lanes (the highest lane of a hash wins)
+                inserted &= hmask;
+                const unsigned mine = peers & inserted;
+                BDF_ASSERT(!hashable || h < 32768u);
+                BDF_ASSERT(nxt > pos && (mm & lit) == 0);
+                if (((inserted >> lane) & 1u) && (mine >> lane) == 1u) table[h] = (pos_t)p;
+                uint32_t bits = 0, nb = 0;
+                if ((mm >> lane) & 1u) {
+                    uint32_t b0, n0, b1, n1;
+                    static_len_code(mylen, b0, n0);
+                    static_off_code(p - mycand, b1, n1);
+                    bits = b0 | b1 << n0;                                       // <= 13 + 18 bits
+                    nb = n0 + n1;
+                } else if (((lit >> lane) & 1u) && p < len) {
+                    static_lit_code(hashable ? (v & 0xFFu) : in[p], bits, nb);
+                }
+                bs.put(bits, nb, lane);
+                pos = nxt;
+                run_mode = lastlen == 258;
+                __syncwarp();
+                continue;
             }
             const uint32_t p = pos + lane;
             const bool hashable = p + 3 <= len;          // the last two positions are never hashed (:1140)

@@ -14,7 +14,7 @@ from test_gpu_fuzz import random_buffer
 
 rng = np.random.default_rng(99)
 bufs = [random_buffer(rng, 65536) for _ in range(150)] + [corpus.corpus_b_stream(k) for k in range(40)]
-for level in (2, 6, 9):
+for level in (1, 2, 6, 9):            # level 1: whole-window rounds or one match per round (BDF_L1_WINDOW)
     for fmt in (0, 2):
         got = bdf.BatchCompressor(level, format=fmt).compress_batch(bufs)
         print("compress", level, fmt, hashlib.sha256(b"\0".join(got)).hexdigest())

@@ -25,13 +25,17 @@ VARIANTS = [
     {"BDF_INFLATE_MODE": "lane", "BDF_INFLATE_PREHDR": "0"},
     {"BDF_INFLATE_SERIAL": "2", "BDF_INFLATE_SPLIT": "2", "BDF_NOS_SPLIT": "0"},
     {"BDF_NOS_WAVE": "1"},
+    # level 1: one match per round (the round-1 parse) on fewer resident CTAs; whole-window rounds without the bucket prefetch
+    {"BDF_L1_WINDOW": "0", "BDF_L1_CTAS_PER_SM": "3"},
+    {"BDF_L1_WINDOW": "1", "BDF_INFLATE_MODE": "group", "BDF_INFLATE_GROUP": "32"},
 ]
 
 
 def run(env):
     e = dict(os.environ)
     for k in ("BDF_HC_KERNEL", "BDF_HC_CTAS_PER_SM", "BDF_INFLATE_MODE", "BDF_INFLATE_GROUP", "BDF_LANE_CFG",
-              "BDF_INFLATE_SPLIT", "BDF_LANE_WARPS", "BDF_INFLATE_PREHDR", "BDF_INFLATE_SERIAL", "BDF_NOS_SPLIT", "BDF_NOS_WAVE"):
+              "BDF_INFLATE_SPLIT", "BDF_LANE_WARPS", "BDF_INFLATE_PREHDR", "BDF_INFLATE_SERIAL", "BDF_NOS_SPLIT", "BDF_NOS_WAVE",
+              "BDF_L1_WINDOW", "BDF_L1_CTAS_PER_SM"):
         e.pop(k, None)
     e.update(env)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "determinism_helper.py")], cwd=ROOT, env=e,
@@ -42,6 +46,6 @@ def run(env):
 
 def test_same_bytes_whatever_the_kernel_choice():
     base = run(VARIANTS[0])
-    assert len(base) == 11
+    assert len(base) == 13
     for v in VARIANTS[1:]:
         assert run(v) == base, v
