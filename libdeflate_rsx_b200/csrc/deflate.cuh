@@ -190,8 +190,10 @@ inline cudaError_t launch_deflate(DeflateArgs a, DeflateScratch &scratch, int sm
         // compare settings
         const char *env = getenv("BDF_L1_CTAS_PER_SM");
         const int l1_ctas_per_sm = env && atoi(env) > 0 && atoi(env) <= 16 ? atoi(env) : BDF_L1_MIN_CTAS;
-        env = getenv("BDF_L1_WINDOW");           // 0 = one match per round (the round-1 parse); bit 0 = whole-window rounds, bits 1 / 2 = bucket prefetch into L1 / L2
-        a.l1_window = env ? atoi(env) : 3;
+        // 0 = one match per round (the round-1 parse); bit 0 = whole-window rounds, bits 1 / 2 = bucket prefetch into
+        // L1 / L2, bit 3 = whole-window rounds also where blocks are split (units above 64 KiB, size estimation)
+        env = getenv("BDF_L1_WINDOW");
+        a.l1_window = env ? atoi(env) : 11;
         const unsigned long long full = (unsigned long long)sm_count * l1_ctas_per_sm;
         const unsigned long long want = ((unsigned long long)a.n + L1_WARPS - 1) / L1_WARPS;
         const unsigned grid = (unsigned)(want < full ? want : full);

@@ -38,7 +38,7 @@ struct DeflateArgs {
     const uint8_t *klass = nullptr;
     uint8_t want = 0;
     int nos_depth = 0;       // levels 10..12: chain depth override for experiments (BDF_NOS_DEPTH), 0 = the level's own
-    int l1_window = 3;       // level 1: bit 0 = whole-window rounds, bits 1 / 2 = next window's buckets prefetched into L1 / L2 (deflate_l1.cuh; BDF_L1_WINDOW)
+    int l1_window = 11;      // level 1: bit 0 = whole-window rounds, bits 1 / 2 = next window's buckets prefetched into L1 / L2, bit 3 = also in the block-split path (deflate_l1.cuh; BDF_L1_WINDOW)
 };
 constexpr unsigned UNIT_FINISH = 1u, UNIT_SYNC = 2u, UNIT_CAP5 = 4u;   // CAP5: 5 more bytes of room (DeflateEncoder, src/stream.rs:66-69)
 __host__ __device__ inline uint64_t unit_cap(uint64_t len, unsigned flags) { return len + (len / 65535 + 1) * 5 + 10 + ((flags & 4u) ? 5 : 0); }

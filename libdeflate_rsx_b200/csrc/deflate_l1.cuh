@@ -8,12 +8,17 @@
 //
 // The parse is inherently serial because only positions where find_match is
 // CALLED enter the table (skip_positions is a no-op, :1231).  One warp owns a
-// stream and speculates 32 consecutive positions at a time as "all literals":
-// each lane probes as if every lower lane had been inserted (same-hash lower
-// lanes are found with match.any), the first lane that really finds a match
-// ends the speculation, lanes up to it commit their table writes, and the
-// literals plus the match are bit-packed with a warp prefix sum.  The result
-// is exactly the serial parse.
+// stream and resolves a WINDOW of 32 consecutive positions per round: every lane
+// reads its bucket as it was before the round and probes as if every lower lane
+// had been inserted (same-hash lower lanes are found with match.any), the warp
+// walks the window from match to match on ballot masks, the lanes that were
+// really probed commit their table writes, and all literals and matches of the
+// window are bit-packed with one warp prefix sum.  The result is exactly the
+// serial parse (lane-level model: tools/l1_window_sim.py, tests/test_l1_window.py).
+// The round-1 form of the round — 32 positions speculated as "all literals", the
+// first lane that really finds a match ends the round — is kept behind
+// BDF_L1_WINDOW=0 (determinism test), and the run-of-maximum-length-matches round
+// takes over after a 258-byte match.
 #pragma once
 #include "deflate_common.cuh"
 
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(L1_WARPS * 32, BDF_L1_MIN_CTAS) deflate_l1_ker
                 __syncwarp();
                 // the position is not a match at all: the literal speculation takes it from here
             }
-            if (!split && a.l1_window) {
+            if ((a.l1_window & 1) && (!split || (a.l1_window & 8))) {
                 // WHOLE-WINDOW ROUND (tools/l1_window_sim.py states it with plain lists and checks it
                 // against the serial parse).  The 32 lanes read their buckets once, as they were
                 // before the round; bucket writes of the round are stood in for by same-hash lower
@@ -298,19 +303,68 @@ __global__ void __launch_bounds__(L1_WARPS * 32, BDF_L1_MIN_CTAS) deflate_l1_ker
                 BDF_ASSERT(!hashable || h < 32768u);
                 BDF_ASSERT(nxt > pos && (mm & lit) == 0);
                 if (((inserted >> lane) & 1u) && (mine >> lane) == 1u) table[h] = (pos_t)p;
+                const bool is_match = (mm >> lane) & 1u;
+                const bool is_lit = !is_match && ((lit >> lane) & 1u) && p < len;
+                const uint32_t byte = hashable ? (v & 0xFFu) : (is_lit ? in[p] : 0u);
+                // Block splitting (units above 64 KiB, size estimation): the statistics see the symbols of
+                // the window in stream order = lane order.  should_end_block can only act once 2048
+                // observations are pending, so a round that cannot reach that is counted in bulk; the others
+                // are replayed symbol by symbol by lane 0 (same rule as the one-match rounds below).
+                uint32_t cut = 0xFFFFFFFFu;                 // lane in front of whose symbol the block ends
+                if (split) {
+                    const unsigned litmask = __ballot_sync(BDF_FULL_MASK, is_lit);
+                    const uint32_t nobs = __popc(litmask) + 2u * __popc(mm);
+                    const unsigned oslot = is_match ? offset_slot_of(p - mycand) : 0u;
+                    const unsigned ocls = oslot < 16 ? 0u : oslot < 24 ? 1u : oslot < 30 ? 2u : 0u;
+                    const uint32_t pending = st.num_new;
+                    __syncwarp();
+                    if (pending + nobs < 2048) {
+                        if (is_lit) atomicAdd(&st.new_obs[byte >> 5], 1u);
+                        if (is_match) { atomicAdd(&st.new_obs[8 + (mylen >= 8)], 1u); atomicAdd(&st.new_obs[10 + ocls], 1u); }
+                        __syncwarp();
+                        if (lane == 0) st.num_new = pending + nobs;
+                    } else {
+                        const uint32_t info = is_match ? ((mylen >= 8 ? 1u : 0u) | ocls << 1) : byte;
+                        for (unsigned rem = litmask | mm; rem; rem &= rem - 1u) {
+                            const unsigned l = __ffs(rem) - 1;
+                            const uint32_t x = __shfl_sync(BDF_FULL_MASK, info, l);
+                            if (lane == 0) {
+                                if (hc_should_end(st, pos + l - block_start, len - (pos + l))) {
+                                    cut = l;                        // at most once per round: 2048 more are needed
+                                    block_start = pos + l;
+                                    for (int c = 0; c < 14; c++) { st.new_obs[c] = 0; st.obs[c] = 0; }
+                                    st.num_new = 0; st.num_obs = 0;
+                                }
+                                if ((mm >> l) & 1u) { st.new_obs[8 + (x & 1u)]++; st.new_obs[10 + (x >> 1)]++; st.num_new += 2; }
+                                else { st.new_obs[x >> 5]++; st.num_new++; }
+                            }
+                        }
+                        cut = __shfl_sync(BDF_FULL_MASK, cut, 0);
+                        block_start = __shfl_sync(BDF_FULL_MASK, block_start, 0);
+                    }
+                    __syncwarp();
+                }
                 uint32_t bits = 0, nb = 0;
-                if ((mm >> lane) & 1u) {
+                if (is_match) {
                     uint32_t b0, n0, b1, n1;
                     static_len_code(mylen, b0, n0);
                     static_off_code(p - mycand, b1, n1);
                     bits = b0 | b1 << n0;                                       // <= 13 + 18 bits
                     nb = n0 + n1;
-                } else if (((lit >> lane) & 1u) && p < len) {
-                    static_lit_code(hashable ? (v & 0xFFu) : in[p], bits, nb);
+                } else if (is_lit) {
+                    static_lit_code(byte, bits, nb);
                 }
-                bs.put(bits, nb, lane);
+                if (cut == 0xFFFFFFFFu) {
+                    bs.put(bits, nb, lane);
+                } else {
+                    bs.put(lane < cut ? bits : 0, lane < cut ? nb : 0, lane);
+                    bs.put1(0, 7, lane);                     // end of block (symbol 256 = 0000000)
+                    bfinal_at = bs.bitpos();
+                    bs.put1(2u, 3, lane);                    // BFINAL = 0 for now, BTYPE = 01
+                    bs.put(lane >= cut ? bits : 0, lane >= cut ? nb : 0, lane);
+                }
                 pos = nxt;
-                run_mode = lastlen == 258;
+                run_mode = !split && lastlen == 258;
                 __syncwarp();
                 continue;
             }
