@@ -40,3 +40,27 @@ def test_window_round_is_the_serial_parse(name, data):
         exp = o.compress(data, 1)
         if exp is not None:                       # None: the static block does not fit the bound (in-band failure)
             assert encode_static(serial) == exp
+
+
+def big_cases():
+    rng = np.random.default_rng(3)
+    het = bytes(corpus.text_stream(1))[:30000] + bytes(corpus.binary_stream(2))[:30000] + \
+        bytes(corpus.lowentropy_stream(3))[:30000] + bytes(corpus.corpus_a_stream(0))[:20000] + \
+        bytes(rng.integers(0, 64, 20000, dtype=np.uint8)) + bytes(corpus.text_stream(4))[:30000]
+    return [("heterogeneous", het),
+            ("text", (bytes(corpus.text_stream(1)) + bytes(corpus.text_stream(7)))[:100000]),
+            ("just_above", bytes(corpus.corpus_b_stream(2)) + b"xyz")]
+
+
+@pytest.mark.parametrize("name,data", big_cases(), ids=[c[0] for c in big_cases()])
+def test_window_rounds_with_block_splitting(name, data):
+    """Inputs above 64 KiB: the window's symbols go to the split statistics in lane order (bulk while
+    no cut is possible, one by one otherwise); blocks and bytes must be the reference's."""
+    from l1_window_sim import serial_blocks, window_blocks
+    blocks = window_blocks(data)
+    assert blocks == serial_blocks(data)
+    bulk, slow = window_blocks.last_rounds
+    assert bulk > slow and (slow > 0 or name == "just_above")
+    if name == "heterogeneous":
+        assert len(blocks) >= 3
+    assert encode_static(None, blocks) == o.compress(data, 1)

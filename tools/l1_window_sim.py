@@ -54,9 +54,10 @@ def serial_tokens(d):
     return out
 
 
-def window_tokens(d, spec_cap=None):
+def window_tokens(d, spec_cap=None, per_round=None):
     """The kernel's round.  spec_cap: the per-lane speculative compare stops there (the kernel
-    finishes longer matches cooperatively); it must not change the result."""
+    finishes longer matches cooperatively); it must not change the result.  per_round: a list that
+    receives (first position, per-lane symbols) of every round."""
     n = len(d)
     table = {}
     out = []
@@ -152,9 +153,115 @@ def window_tokens(d, spec_cap=None):
             if inserted >> l & 1:
                 table[h[l]] = p[l]
         out.extend(x for x in kind if x is not None)
+        if per_round is not None:
+            per_round.append((pos, kind))
         pos = nxt
     window_tokens.last_steps = (static_steps, dynamic_steps)
     return out, rounds
+
+
+# --- block splitting on top of the window rounds (units above 64 KiB, size estimation):
+# BlockSplitStats::should_end_block, src/compress/mod.rs:387-415; compress_greedy_block's level-1
+# loop asks it in front of every symbol (:1531-1564)
+MIN_BLOCK_LENGTH = 5000
+SOFT_MAX_BLOCK_LENGTH = 300000
+
+
+class SplitStats:
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.new_obs = [0] * 14
+        self.obs = [0] * 14
+        self.num_new = 0
+        self.num = 0
+
+    def literal(self, b):
+        self.new_obs[b >> 5] += 1
+        self.num_new += 1
+
+    def match(self, length, offset):
+        slot = max(i for i in range(30) if _OFF_BASE[i] <= offset)
+        self.new_obs[8 + (length >= 8)] += 1
+        self.new_obs[10 + (0 if slot < 16 else 1 if slot < 24 else 2 if slot < 30 else 0)] += 1
+        self.num_new += 2
+
+    def should_end(self, block_len, remaining):
+        if self.num_new < 2048 and block_len < SOFT_MAX_BLOCK_LENGTH:
+            return False
+        if remaining <= MIN_BLOCK_LENGTH:
+            return False
+        if block_len >= SOFT_MAX_BLOCK_LENGTH:
+            return True
+        if block_len >= MIN_BLOCK_LENGTH:
+            if self.num:
+                lg_all, lg_new = self.num.bit_length() - 1, self.num_new.bit_length() - 1
+                old_bits = new_bits = 0
+                for o_, k in zip(self.obs, self.new_obs):
+                    if k:
+                        lo, ln = (o_ + 1).bit_length() - 1, (k + 1).bit_length() - 1
+                        old_bits += k * max(lg_all - lo, 0)
+                        new_bits += k * max(lg_new - ln, 0)
+                if old_bits - new_bits > block_len // 16:
+                    return True
+            self.obs = [a + b for a, b in zip(self.obs, self.new_obs)]
+            self.new_obs = [0] * 14
+            self.num += self.num_new
+            self.num_new = 0
+        return False
+
+
+def serial_blocks(d):
+    """The reference's level-1 block loop on an input above 64 KiB: a list of token lists."""
+    n = len(d)
+    tokens = serial_tokens(d)
+    blocks, cur, st, p, start = [], [], SplitStats(), 0, 0
+    for t in tokens:
+        if st.should_end(p - start, n - p):
+            blocks.append(cur)
+            cur, start = [], p
+            st.reset()
+        if isinstance(t, tuple):
+            st.match(*t)
+            p += t[0]
+        else:
+            st.literal(t)
+            p += 1
+        cur.append(t)
+    blocks.append(cur)
+    return blocks
+
+
+def window_blocks(d, spec_cap=16):
+    """The kernel's way: the symbols of a window go to the statistics in lane order — in bulk while
+    the round cannot bring 2048 observations together, one by one otherwise — and a cut lands in
+    front of the symbol of one lane."""
+    n = len(d)
+    rounds = []
+    window_tokens(d, spec_cap, rounds)
+    blocks, cur, st, start = [], [], SplitStats(), 0
+    bulk = slow = 0
+    for pos, kind in rounds:
+        syms = [(l, t) for l, t in enumerate(kind) if t is not None]
+        nobs = sum(2 if isinstance(t, tuple) else 1 for _, t in syms)
+        if st.num_new + nobs < 2048:
+            bulk += 1
+            for _, t in syms:                       # order does not matter here: plain counters
+                st.match(*t) if isinstance(t, tuple) else st.literal(t)
+            cur.extend(t for _, t in syms)
+        else:
+            slow += 1
+            for l, t in syms:
+                if st.should_end(pos + l - start, n - (pos + l)):
+                    blocks.append(cur)
+                    cur, start = [], pos + l
+                    st.reset()
+                st.match(*t) if isinstance(t, tuple) else st.literal(t)
+                cur.append(t)
+    blocks.append(cur)
+    window_blocks.last_rounds = (bulk, slow)
+    return blocks
 
 
 # --- static-Huffman bit stream (RFC 1951 3.2.6), for the comparison with the oracle's bytes
@@ -169,7 +276,8 @@ def _rev(x, n):
     return int(format(x, "0%db" % n)[::-1], 2)
 
 
-def encode_static(tokens):
+def encode_static(tokens, blocks=None):
+    """One final static block of `tokens`, or the given list of blocks (the last one final)."""
     acc, nbits = 0, 0
 
     def put(bits, n):
@@ -187,17 +295,19 @@ def encode_static(tokens):
         else:
             put(_rev(0xC0 + sym - 280, 8), 8)
 
-    put(3, 3)                                    # BFINAL = 1, BTYPE = 01
-    for t in tokens:
-        if isinstance(t, tuple):
-            ln, off = t
-            s = max(i for i in range(29) if _LEN_BASE[i] <= ln)
-            litlen(257 + s)
-            put(ln - _LEN_BASE[s], _LEN_EXTRA[s])
-            s = max(i for i in range(30) if _OFF_BASE[i] <= off)
-            put(_rev(s, 5), 5)
-            put(off - _OFF_BASE[s], _OFF_EXTRA[s])
-        else:
-            litlen(t)
-    litlen(256)
+    for bi, toks in enumerate([tokens] if blocks is None else blocks):
+        last = blocks is None or bi == len(blocks) - 1
+        put((1 if last else 0) | 2, 3)              # BFINAL, BTYPE = 01
+        for t in toks:
+            if isinstance(t, tuple):
+                ln, off = t
+                s = max(i for i in range(29) if _LEN_BASE[i] <= ln)
+                litlen(257 + s)
+                put(ln - _LEN_BASE[s], _LEN_EXTRA[s])
+                s = max(i for i in range(30) if _OFF_BASE[i] <= off)
+                put(_rev(s, 5), 5)
+                put(off - _OFF_BASE[s], _OFF_EXTRA[s])
+            else:
+                litlen(t)
+        litlen(256)
     return acc.to_bytes((nbits + 7) // 8, "little")
