@@ -29,9 +29,11 @@ constexpr int L1_RUN_BATCH = 8;                  // matches of a speculated run 
 constexpr uint32_t L1_SPEC_CAP = 16;             // bytes of a match every lane measures ahead of the window walk
 
 // The hash table of each stream (last position per bucket, all-ones = empty; 16-bit positions
-// for the 64 KiB instance, 32-bit for the 256 KiB one) lives in a per-warp global slab that
-// stays L2-resident while the stream is parsed: in shared memory it would cap the SM at three
-// streams, and this parse is a chain of dependent probes that only many streams in flight can hide.
+// for the 64 KiB instance, 32-bit for the 256 KiB one) lives in a per-warp global slab behind
+// L1 / L2: in shared memory it would cap the SM at three streams, and this parse is a chain of
+// dependent probes that only many streams in flight can hide (measured: 8 / 6 / 4 / 2 CTAs per SM
+// = 35 / 27 / 22 / 14 GB/s on text, profiles/r4_l1_window_probe.txt).  With a full grid the tables
+// (310 MB) and inputs exceed the L2, so the probes run at the memory system's random-sector rate.
 template <bool BIG>
 struct L1Cfg {
     using pos_t = typename std::conditional<BIG, uint32_t, uint16_t>::type;
@@ -223,8 +225,9 @@ __global__ void __launch_bounds__(L1_WARPS * 32, BDF_L1_MIN_CTAS) deflate_l1_ker
                 const unsigned hmask = __ballot_sync(BDF_FULL_MASK, hashable);
                 uint32_t tc = CFG::EMPTY;
                 if (hashable) tc = table[h];
-                // (experiment, bits 1 / 2 of BDF_L1_WINDOW) the buckets of the NEXT window are prefetched while this
-                // one is worked on: its bytes are requested here and have arrived once the bucket above has
+                // The buckets of the NEXT window are prefetched while this one is worked on (bits 1 / 2 of
+                // BDF_L1_WINDOW: into L1, the default, or L2; +1-4 %): its bytes are requested here and have
+                // arrived once the bucket above has
                 uint32_t vn = 0;
                 const bool pn = (a.l1_window & 6) && p + 35 <= len;
                 if (pn) vn = ld24(in + p + 32);
