@@ -208,7 +208,7 @@ def cpu_compress(o, flat, in_off, n, level, fmt, min_seconds):
     return int(sub_off[-1]) / best / 1e9, cores, reps, (out, out_off, out_size)
 
 
-def l1_text_probe(env, d_slab, d_slab_off, d_size, d_stat, bound, steps, n_max):
+def l1_text_probe(env, d_slab, d_slab_off, d_size, d_stat, bound, steps, n_max, with_cpu=False, cpu_seconds=3.0):
     """Level 1 on NON-periodic data (corpus A is a run of 258-byte matches, the easy case of this parse):
     8192 x 64 KiB of the text kind of corpus B per GPU, 64 distinct streams, byte-identical to the
     oracle, device-resident (CUDA events)."""
@@ -247,10 +247,18 @@ def l1_text_probe(env, d_slab, d_slab_off, d_size, d_stat, bound, steps, n_max):
         env["dist"].all_reduce(t, op=env["dist"].ReduceOp.MAX)
     ms = float(t.item())
     comp = int(sizes.sum())
-    return {"workload": f"compress {n} x 64 KiB of text (corpus B's text kind) per GPU at level 1, raw DEFLATE; byte-identical to the oracle",
-            "unit": "GB/s (uncompressed)", "value": world * n * STREAM / (ms * 1e-3) / 1e9, "kernel_ms": ms, "steps": steps,
-            "ratio": n * STREAM / comp,
-            "roofline": roofline("bdf::deflate_l1_kernel (whole-window rounds)", n * STREAM + comp, ms, n, "deflate_l1_text_window")}
+    sec = {"workload": f"compress {n} x 64 KiB of text (corpus B's text kind) per GPU at level 1, raw DEFLATE; byte-identical to the oracle",
+           "unit": "GB/s (uncompressed)", "value": world * n * STREAM / (ms * 1e-3) / 1e9, "kernel_ms": ms, "steps": steps,
+           "ratio": n * STREAM / comp,
+           "roofline": roofline("bdf::deflate_l1_kernel (whole-window rounds)", n * STREAM + comp, ms, n, "deflate_l1_text_window")}
+    if with_cpu:
+        ns = min(n, 1024)
+        h_flat = np.frombuffer(b"".join(plain) * (ns // 64), dtype=np.uint8)
+        h_off = np.arange(ns + 1, dtype=np.uint64) * np.uint64(STREAM)
+        v, cores, reps, _ = cpu_compress(o, h_flat, h_off, ns, 1, o.RAW, min(cpu_seconds, 3.0))
+        sec["cpu_baseline"] = {"value": v, "unit": "GB/s", "cores": cores, "kind": "port",
+                               "sample": f"{ns} of the {n} streams ({ns * STREAM >> 20} MiB), best of {reps} passes, " + ORACLE_NOTE}
+    return sec
 
 
 def compress_section(env, level, n, steps, e2e_steps, cpu_sample, cpu_seconds, with_cpu):
@@ -307,7 +315,8 @@ def compress_section(env, level, n, steps, e2e_steps, cpu_sample, cpu_seconds, w
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     ubytes = n * STREAM
-    text = l1_text_probe(env, d_slab, d_slab_off, d_size, d_stat, bound, steps, n) if level == 1 and n >= 64 else None
+    text = (l1_text_probe(env, d_slab, d_slab_off, d_size, d_stat, bound, steps, n, with_cpu, cpu_seconds)
+            if level == 1 and n >= 64 else None)
     del d_slab
     torch.cuda.empty_cache()
 
